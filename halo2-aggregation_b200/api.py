@@ -1,0 +1,393 @@
+"""ctypes binding of libh2agg.so and a host-side mirror of the reference-facing interface.
+
+Reference interface mirrored (all [UPSTREAM-INFERRED] signatures of the `halo2`
+dependency pinned at Cargo.toml:12):
+  best_multiexp(coeffs, bases) -> point          call sites: examples/simple-example.rs:638-640
+  best_fft(a, omega, log_n)                       domain touched at src/verifier.rs:252,431
+  EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff, get_omega}
+  MultiopenChip::calc_witness native values       src/multiopen.rs:271-509 -> verify_accumulate
+  TranscriptChip / Blake2bWrite                   src/transcript.rs:66-129 -> Transcript
+Buffers are numpy uint8 arrays in the library's wire layout (32-byte Montgomery field elements,
+64-byte affine points).
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_u8p = ctypes.c_void_p
+c_sz = ctypes.c_size_t
+
+
+class H2AError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("h2agg error %d: %s" % (code, msg))
+        self.code = code
+
+
+def library_path():
+    return os.path.join(_HERE, "libh2agg.so")
+
+
+def header_path():
+    return os.path.join(os.path.dirname(_HERE), "include", "h2agg.h")
+
+
+def declared_symbols():
+    """Every function include/h2agg.h declares."""
+    with open(header_path()) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(h2a_[a-z0-9_]+)\s*\(", text)))
+
+
+def load_library():
+    """Loads libh2agg.so; fails loudly when it has not been built (no fallback of any kind)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise H2AError(-3, "libh2agg.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(path)
+    lib.h2a_last_error.restype = ctypes.c_char_p
+    lib.h2a_stream.restype = ctypes.c_void_p
+    lib.h2a_phase_name.restype = ctypes.c_char_p
+    lib.h2a_launch_count.restype = ctypes.c_uint64
+    lib.h2a_bases_len.restype = c_sz
+    lib.h2a_transcript_new.restype = ctypes.c_void_p
+    lib.h2a_transcript_free.restype = None
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return ctypes.c_void_p(a)
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _bytes(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def fr_root_of_unity(k):
+    out = np.zeros(32, np.uint8)
+    rc = load_library().h2a_fr_root_of_unity(ctypes.c_uint32(k), _ptr(out))
+    if rc != 0:
+        raise H2AError(rc, "root_of_unity(%d)" % k)
+    return out
+
+
+def g1_sum(points):
+    pts = _bytes(points)
+    out = np.zeros(64, np.uint8)
+    rc = load_library().h2a_g1_sum(_ptr(pts), c_sz(pts.size // 64), _ptr(out))
+    if rc != 0:
+        raise H2AError(rc, "g1_sum")
+    return out
+
+
+class Context:
+    """One per GPU / process (h2a_init)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.h2a_init(ctypes.byref(h), int(device))
+        if rc != 0:
+            raise H2AError(rc, "h2a_init(device=%d) failed: no usable sm_100 CUDA device (there is no CPU fallback)" % device)
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.h2a_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise H2AError(rc, (self.lib.h2a_last_error(self.h) or b"").decode())
+
+    # ---- plumbing
+    @property
+    def stream(self):
+        return self.lib.h2a_stream(self.h)
+
+    def sync(self):
+        self._check(self.lib.h2a_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.h2a_launch_count(self.h))
+
+    def dev_alloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(self.lib.h2a_dev_alloc(self.h, c_sz(nbytes), ctypes.byref(p)))
+        return p.value
+
+    def dev_free(self, p):
+        self._check(self.lib.h2a_dev_free(self.h, ctypes.c_void_p(p)))
+
+    def h2d(self, dev, host):
+        host = _bytes(host)
+        self._check(self.lib.h2a_copy_h2d(self.h, ctypes.c_void_p(dev), _ptr(host), c_sz(host.size)))
+
+    def d2h(self, dev, nbytes):
+        out = np.zeros(nbytes, np.uint8)
+        self._check(self.lib.h2a_copy_d2h(self.h, _ptr(out), ctypes.c_void_p(dev), c_sz(nbytes)))
+        return out
+
+    def set_profiling(self, on):
+        self._check(self.lib.h2a_set_profiling(self.h, int(bool(on))))
+
+    def last_phases(self, kind=0):
+        buf = (ctypes.c_float * 16)()
+        n = self.lib.h2a_last_phase_ms(self.h, buf, 16)
+        return [((self.lib.h2a_phase_name(kind, i) or b"").decode(), float(buf[i])) for i in range(max(n, 0))]
+
+    def bench_imad(self):
+        v = ctypes.c_double()
+        self._check(self.lib.h2a_bench_imad(self.h, ctypes.byref(v)))
+        return v.value
+
+    def bench_modmul(self):
+        v = ctypes.c_double()
+        self._check(self.lib.h2a_bench_modmul(self.h, ctypes.byref(v)))
+        return v.value
+
+    # ---- synthetic inputs
+    def gen_scalars_dev(self, seed, n, dev, first=0):
+        self._check(self.lib.h2a_gen_scalars_dev(self.h, ctypes.c_uint64(seed), c_sz(first), c_sz(n), ctypes.c_void_p(dev)))
+
+    def gen_bases_dev(self, seed, n, dev, first=0):
+        self._check(self.lib.h2a_gen_bases_dev(self.h, ctypes.c_uint64(seed), c_sz(first), c_sz(n), ctypes.c_void_p(dev)))
+
+    # ---- MSM
+    def upload_bases(self, affine):
+        affine = _bytes(affine)
+        h = ctypes.c_void_p()
+        self._check(self.lib.h2a_bases_upload(self.h, _ptr(affine), c_sz(affine.size // 64), ctypes.byref(h)))
+        return Bases(self, h)
+
+    def bases_from_device(self, dev, n):
+        h = ctypes.c_void_p()
+        self._check(self.lib.h2a_bases_from_device(self.h, ctypes.c_void_p(dev), c_sz(n), ctypes.byref(h)))
+        return Bases(self, h)
+
+    def set_msm_window(self, c):
+        self._check(self.lib.h2a_msm_set_window(self.h, int(c)))
+
+    def msm(self, bases, scalars, offset=0):
+        """best_multiexp over resident bases, host scalars.  Returns the 64-byte affine result."""
+        scalars = _bytes(scalars)
+        out = np.zeros(64, np.uint8)
+        self._check(self.lib.h2a_msm_g1(self.h, bases.h, c_sz(offset), _ptr(scalars), c_sz(scalars.size // 32), _ptr(out)))
+        return out
+
+    def msm_dev(self, bases, d_scalars, n, offset=0):
+        out = np.zeros(64, np.uint8)
+        self._check(self.lib.h2a_msm_g1_dev(self.h, bases.h, c_sz(offset), ctypes.c_void_p(d_scalars), c_sz(n), _ptr(out)))
+        return out
+
+    def msm_batch(self, bases, columns):
+        cols = [_bytes(c) for c in columns]
+        m = len(cols)
+        ptrs = (ctypes.c_void_p * m)(*[c.ctypes.data for c in cols])
+        ns = (c_sz * m)(*[c.size // 32 for c in cols])
+        out = np.zeros(64 * m, np.uint8)
+        self._check(self.lib.h2a_msm_g1_batch(self.h, bases.h, ptrs, ns, m, _ptr(out)))
+        return out.reshape(m, 64)
+
+    def msm_adhoc(self, bases_affine, scalars):
+        b, s = _bytes(bases_affine), _bytes(scalars)
+        if b.size // 64 != s.size // 32:
+            raise H2AError(-1, "msm_adhoc: %d bases vs %d scalars" % (b.size // 64, s.size // 32))
+        out = np.zeros(64, np.uint8)
+        self._check(self.lib.h2a_msm_g1_adhoc(self.h, _ptr(b), _ptr(s), c_sz(s.size // 32), _ptr(out)))
+        return out
+
+    # ---- NTT
+    def ntt(self, a, log_n, omega, inverse=False, coset_shift=None):
+        a = _bytes(a).copy()
+        if a.size != 32 << log_n:
+            raise H2AError(-1, "ntt: buffer has %d bytes, expected %d" % (a.size, 32 << log_n))
+        cs = _bytes(coset_shift) if coset_shift is not None else None
+        self._check(self.lib.h2a_ntt(self.h, _ptr(a), ctypes.c_uint32(log_n), _ptr(_bytes(omega)), int(bool(inverse)), _ptr(cs)))
+        return a
+
+    def ntt_dev(self, d_a, log_n, omega, inverse=False, coset_shift=None):
+        cs = _bytes(coset_shift) if coset_shift is not None else None
+        self._check(self.lib.h2a_ntt_dev(self.h, ctypes.c_void_p(d_a), ctypes.c_uint32(log_n), _ptr(_bytes(omega)),
+                                         int(bool(inverse)), _ptr(cs)))
+
+    def coeff_to_extended(self, coeffs, k, ext_k, coset_shift):
+        coeffs = _bytes(coeffs)
+        if coeffs.size != 32 << k:
+            raise H2AError(-1, "coeff_to_extended: buffer has %d bytes, expected %d" % (coeffs.size, 32 << k))
+        out = np.zeros(32 << ext_k, np.uint8)
+        self._check(self.lib.h2a_coeff_to_extended(self.h, _ptr(coeffs), ctypes.c_uint32(k), ctypes.c_uint32(ext_k),
+                                                   _ptr(_bytes(coset_shift)), _ptr(out)))
+        return out
+
+    def extended_to_coeff(self, ext, ext_k, coset_shift):
+        ext = _bytes(ext).copy()
+        self._check(self.lib.h2a_extended_to_coeff(self.h, _ptr(ext), ctypes.c_uint32(ext_k), _ptr(_bytes(coset_shift))))
+        return ext
+
+    # ---- verifier glue
+    def verify_accumulate(self, commitments, rotations, evals, ws, x, u, v, omega, g1):
+        c, e, w = _bytes(commitments), _bytes(evals), _bytes(ws)
+        rot = np.ascontiguousarray(rotations, dtype=np.int32)
+        out = np.zeros(256, np.uint8)
+        self._check(self.lib.h2a_verify_accumulate(self.h, _ptr(c), _ptr(rot), _ptr(e), c_sz(rot.size), _ptr(w),
+                                                   c_sz(w.size // 64), _ptr(_bytes(x)), _ptr(_bytes(u)), _ptr(_bytes(v)),
+                                                   _ptr(_bytes(omega)), _ptr(_bytes(g1)), _ptr(out)))
+        return out
+
+    def verify_accumulate_batch(self, proofs, omega, g1):
+        """proofs: list of dicts with commitments, rotations, evals, ws, x, u, v."""
+        n = len(proofs)
+        c = np.concatenate([_bytes(p["commitments"]) for p in proofs]) if n else np.zeros(0, np.uint8)
+        r = np.concatenate([np.asarray(p["rotations"], dtype=np.int32) for p in proofs]) if n else np.zeros(0, np.int32)
+        e = np.concatenate([_bytes(p["evals"]) for p in proofs]) if n else np.zeros(0, np.uint8)
+        w = np.concatenate([_bytes(p["ws"]) for p in proofs]) if n else np.zeros(0, np.uint8)
+        xuv = np.concatenate([np.concatenate([_bytes(p["x"]), _bytes(p["u"]), _bytes(p["v"])]) for p in proofs]) if n else np.zeros(0, np.uint8)
+        q_off = np.zeros(n + 1, dtype=np.uint64)
+        w_off = np.zeros(n + 1, dtype=np.uint64)
+        for i, p in enumerate(proofs):
+            q_off[i + 1] = q_off[i] + len(p["rotations"])
+            w_off[i + 1] = w_off[i] + _bytes(p["ws"]).size // 64
+        out = np.zeros(256 * n, np.uint8)
+        self._check(self.lib.h2a_verify_accumulate_batch(self.h, c_sz(n), _ptr(c), _ptr(np.ascontiguousarray(r)), _ptr(e), _ptr(q_off),
+                                                         _ptr(w), _ptr(w_off), _ptr(xuv), _ptr(_bytes(omega)), _ptr(_bytes(g1)),
+                                                         _ptr(out)))
+        return out.reshape(n, 256)
+
+    def fold_h(self, h_pieces, xn):
+        h = _bytes(h_pieces)
+        out = np.zeros(64, np.uint8)
+        self._check(self.lib.h2a_fold_h(self.h, _ptr(h), c_sz(h.size // 64), _ptr(_bytes(xn)), _ptr(out)))
+        return out
+
+    # ---- test hooks
+    FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5}
+
+    def field_op(self, field, op, a, b=None):
+        a = _bytes(a)
+        bb = _bytes(b) if b is not None else None
+        out = np.zeros(a.size, np.uint8)
+        self._check(self.lib.h2a_field_op(self.h, int(field), self.FIELD_OPS[op], _ptr(a), _ptr(bb), _ptr(out), c_sz(a.size // 32)))
+        return out
+
+    def g1_op(self, op, a, b=None):
+        a = _bytes(a)
+        bb = _bytes(b) if b is not None else None
+        out = np.zeros(a.size, np.uint8)
+        self._check(self.lib.h2a_g1_op(self.h, {"add": 0, "dbl": 1, "dbl_add": 2}[op], _ptr(a), _ptr(bb), _ptr(out), c_sz(a.size // 64)))
+        return out
+
+
+class Bases:
+    """Device-resident affine bases (`Params.g` / `Params.g_lagrange`)."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    def __len__(self):
+        return int(self.ctx.lib.h2a_bases_len(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx._check(self.ctx.lib.h2a_bases_free(self.ctx.h, self.h))
+            self.h = None
+
+
+class Transcript:
+    """Blake2bWrite/Blake2bRead with Challenge255 (src/transcript.rs:58,72,105-107,122-124)."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self.h = ctypes.c_void_p(self.lib.h2a_transcript_new())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.h2a_transcript_free(self.h)
+            self.h = None
+
+    def common_point(self, p):
+        rc = self.lib.h2a_transcript_common_point(self.h, _ptr(_bytes(p)))
+        if rc != 0:
+            raise H2AError(rc, "common_point: identity or null")
+
+    def common_scalar(self, s):
+        rc = self.lib.h2a_transcript_common_scalar(self.h, _ptr(_bytes(s)))
+        if rc != 0:
+            raise H2AError(rc, "common_scalar")
+
+    def squeeze_challenge(self):
+        out = np.zeros(32, np.uint8)
+        rc = self.lib.h2a_transcript_squeeze_challenge(self.h, _ptr(out))
+        if rc != 0:
+            raise H2AError(rc, "squeeze_challenge")
+        return out
+
+
+# ---- free functions named after the dependency functions they replace
+def best_multiexp(ctx, coeffs, bases):
+    """halo2 `arithmetic::best_multiexp(coeffs, bases)`; `bases` is a Bases handle or a host array."""
+    if isinstance(bases, Bases):
+        return ctx.msm(bases, coeffs)
+    return ctx.msm_adhoc(bases, coeffs)
+
+
+def best_fft(ctx, a, omega, log_n):
+    """halo2 `arithmetic::best_fft(a, omega, log_n)` (returns the transformed copy)."""
+    return ctx.ntt(a, log_n, omega)
+
+
+class EvaluationDomain:
+    """Mirror of halo2 `poly::EvaluationDomain` for the methods on the hot path.
+
+    j = cs.degree(); quotient_poly_degree = j - 1; extended_k = smallest with 2^extended_k >= n*(j-1).
+    The coset generator is a parameter (the dependency's ZETA is not pinned)."""
+
+    def __init__(self, ctx, j, k, coset_shift):
+        self.ctx, self.k = ctx, k
+        self.quotient_poly_degree = j - 1
+        ext = k
+        while (1 << ext) < (1 << k) * (j - 1):
+            ext += 1
+        self.extended_k = ext
+        self.omega = fr_root_of_unity(k)
+        self.extended_omega = fr_root_of_unity(ext)
+        self.coset_shift = _bytes(coset_shift)
+
+    def get_omega(self):
+        return self.omega
+
+    def get_quotient_poly_degree(self):
+        return self.quotient_poly_degree
+
+    def lagrange_to_coeff(self, a):
+        return self.ctx.ntt(a, self.k, self.omega, inverse=True)
+
+    def coeff_to_lagrange(self, a):
+        return self.ctx.ntt(a, self.k, self.omega)
+
+    def coeff_to_extended(self, a):
+        return self.ctx.coeff_to_extended(a, self.k, self.extended_k, self.coset_shift)
+
+    def extended_to_coeff(self, a):
+        return self.ctx.extended_to_coeff(a, self.extended_k, self.coset_shift)

@@ -1,0 +1,183 @@
+// abi.cu — the MSM / NTT entry points of include/h2agg.h: argument checks, host<->device staging,
+// and dispatch to the kernels in msm.cu / ntt.cu.
+#include <cstring>
+
+#include "ctx.hpp"
+#include "host_bn254.hpp"
+
+int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
+                const uint8_t omega[32], int inverse, const uint8_t* coset_shift);
+int h2a_small_msm(h2a_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, const uint32_t* sum_offsets, size_t n_sums,
+                  uint8_t* out_affine);
+
+constexpr size_t SMALL_MSM_MAX = 2048;  // below this an MSM is one block of the small-MSM kernel
+
+extern "C" {
+
+// ------------------------------------------------------------------ bases
+int h2a_bases_upload(h2a_ctx* ctx, const uint8_t* affine_xy, size_t n, h2a_bases** out) {
+    if (!ctx || !out || (!affine_xy && n)) return H2A_ERR_INVALID;
+    h2a_bases* b = new h2a_bases();
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n ? n * 64 : 64);
+    if (e != cudaSuccess) {
+        delete b;
+        H2A_FAIL(ctx, H2A_ERR_OOM, "bases_upload: cudaMalloc(%zu): %s", n * 64, cudaGetErrorString(e));
+    }
+    if (n) {
+        e = cudaMemcpyAsync(d, affine_xy, n * 64, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(d);
+            delete b;
+            H2A_FAIL(ctx, H2A_ERR_CUDA, "bases_upload: copy: %s", cudaGetErrorString(e));
+        }
+    }
+    b->d = (const uint8_t*)d;
+    b->n = n;
+    b->owned = true;
+    *out = b;
+    return H2A_OK;
+}
+int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_bases** out) {
+    if (!ctx || !out || (!d_affine_xy && n)) return H2A_ERR_INVALID;
+    h2a_bases* b = new h2a_bases();
+    b->d = (const uint8_t*)d_affine_xy;
+    b->n = n;
+    b->owned = false;
+    *out = b;
+    return H2A_OK;
+}
+int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases) {
+    if (!ctx || !bases) return H2A_ERR_INVALID;
+    if (bases->owned && bases->d) {
+        H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        H2A_CUDA(ctx, cudaFree((void*)bases->d));
+    }
+    delete bases;
+    return H2A_OK;
+}
+size_t h2a_bases_len(const h2a_bases* bases) { return bases ? bases->n : 0; }
+
+// ------------------------------------------------------------------ MSM
+int h2a_msm_set_window(h2a_ctx* ctx, int c) {
+    if (!ctx || (c != 0 && (c < 6 || c > 20))) return H2A_ERR_INVALID;
+    ctx->msm_window_override = c;
+    return H2A_OK;
+}
+
+int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                   uint8_t out_affine[64]) {
+    if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;
+    if (offset > bases->n || n > bases->n - offset)
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
+    return h2a_msm_run(ctx, bases->d + 64 * offset, (const uint8_t*)d_scalars, n, out_affine);
+}
+
+int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
+               uint8_t out_affine[64]) {
+    if (!ctx || !bases || !out_affine || (!scalars && n)) return H2A_ERR_INVALID;
+    if (offset > bases->n || n > bases->n - offset)
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
+    if (n == 0) {
+        memset(out_affine, 0, 64);
+        return H2A_OK;
+    }
+    H2A_TRY(h2a_reserve(ctx, ctx->scalars, n * 32));
+    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return h2a_msm_run(ctx, bases->d + 64 * offset, (const uint8_t*)ctx->scalars.p, n, out_affine);
+}
+
+int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,
+                     uint8_t* out_affine) {
+    if (!ctx || !bases || !scalars || !n || !out_affine || m < 0) return H2A_ERR_INVALID;
+    for (int j = 0; j < m; j++) H2A_TRY(h2a_msm_g1(ctx, bases, 0, scalars[j], n[j], out_affine + 64 * j));
+    return H2A_OK;
+}
+
+int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* scalars, size_t n, uint8_t out_affine[64]) {
+    if (!ctx || !out_affine || ((!bases_affine || !scalars) && n)) return H2A_ERR_INVALID;
+    if (n == 0) {
+        memset(out_affine, 0, 64);
+        return H2A_OK;
+    }
+    if (n <= SMALL_MSM_MAX) {
+        uint32_t offs[2] = {0, (uint32_t)n};
+        return h2a_small_msm(ctx, bases_affine, scalars, offs, 1, out_affine);
+    }
+    h2a_bases* b = nullptr;
+    H2A_TRY(h2a_bases_upload(ctx, bases_affine, n, &b));
+    int rc = h2a_msm_g1(ctx, b, 0, scalars, n, out_affine);
+    h2a_bases_free(ctx, b);
+    return rc;
+}
+
+int h2a_g1_sum(const uint8_t* points_affine, size_t m, uint8_t out_affine[64]) {
+    if (!out_affine || (!points_affine && m)) return H2A_ERR_INVALID;
+    using namespace h2a_host;
+    PointX acc = px_identity();
+    for (size_t i = 0; i < m; i++) acc = px_add(acc, px_from_affine(affine_load(points_affine + 64 * i)));
+    affine_store(out_affine, px_to_affine(acc));
+    return H2A_OK;
+}
+
+// ------------------------------------------------------------------ NTT
+int h2a_fr_root_of_unity(uint32_t k, uint8_t out[32]) {
+    if (!out || k > 28) return H2A_ERR_INVALID;
+    h2a_host::fr_store(out, h2a_host::fr_root_of_unity((int)k));
+    return H2A_OK;
+}
+
+int h2a_ntt_dev(h2a_ctx* ctx, void* d_a, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
+    if (!ctx || !d_a || !omega) return H2A_ERR_INVALID;
+    if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
+    const size_t bytes = 32ull << log_n;
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_b, bytes));
+    H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)d_a, 1u << log_n, (uint8_t*)d_a, (uint8_t*)ctx->ntt_b.p, log_n, omega, inverse,
+                        coset_shift));
+    H2A_CUDA(ctx, cudaMemcpyAsync(d_a, ctx->ntt_b.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
+
+int h2a_ntt(h2a_ctx* ctx, uint8_t* a, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
+    if (!ctx || !a || !omega) return H2A_ERR_INVALID;
+    if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
+    const size_t bytes = 32ull << log_n;
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_a, bytes));
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_b, bytes));
+    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->ntt_a.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)ctx->ntt_a.p, 1u << log_n, (uint8_t*)ctx->ntt_a.p, (uint8_t*)ctx->ntt_b.p,
+                        log_n, omega, inverse, coset_shift));
+    H2A_CUDA(ctx, cudaMemcpyAsync(a, ctx->ntt_b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
+
+int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint32_t ext_k, const uint8_t coset_shift[32],
+                          uint8_t* out) {
+    if (!ctx || !coeffs || !out || !coset_shift) return H2A_ERR_INVALID;
+    if (k < 1 || ext_k < k || ext_k > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "coeff_to_extended: k=%u ext_k=%u", k, ext_k);
+    const size_t in_bytes = 32ull << k, out_bytes = 32ull << ext_k;
+    H2A_TRY(h2a_reserve(ctx, ctx->scalars, in_bytes));
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_a, out_bytes));
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_b, out_bytes));
+    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->scalars.p, coeffs, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t omega[32];
+    h2a_fr_root_of_unity(ext_k, omega);
+    H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)ctx->scalars.p, 1u << k, (uint8_t*)ctx->ntt_a.p, (uint8_t*)ctx->ntt_b.p, ext_k,
+                        omega, 0, coset_shift));
+    H2A_CUDA(ctx, cudaMemcpyAsync(out, ctx->ntt_b.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
+
+int h2a_extended_to_coeff(h2a_ctx* ctx, uint8_t* ext, uint32_t ext_k, const uint8_t coset_shift[32]) {
+    if (!ctx || !ext || !coset_shift) return H2A_ERR_INVALID;
+    uint8_t omega[32];
+    if (h2a_fr_root_of_unity(ext_k, omega) != H2A_OK || ext_k < 1)
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "extended_to_coeff: ext_k=%u", ext_k);
+    return h2a_ntt(ctx, ext, ext_k, omega, 1, coset_shift);
+}
+
+}  // extern "C"

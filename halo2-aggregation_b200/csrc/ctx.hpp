@@ -1,0 +1,94 @@
+// ctx.hpp — the library context behind the opaque `h2a_ctx` of include/h2agg.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/h2agg.h"
+
+// A growable device buffer owned by the ctx (workspace that persists across calls so the hot path
+// does no cudaMalloc after warm-up).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct NttTables;  // ntt.cu
+
+struct h2a_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int msm_window_override = 0;
+
+    // profiling
+    bool profiling = false;
+    int last_kind = 0;  // 0 msm, 1 ntt
+    std::vector<cudaEvent_t> ev;
+    int ev_used = 0;
+    std::vector<float> phase_ms;
+
+    // MSM workspace
+    DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc;
+    void* pinned = nullptr;  // small pinned staging area for results
+    size_t pinned_cap = 0;
+
+    // NTT workspace
+    DevBuf ntt_a, ntt_b;
+    std::map<uint32_t, NttTables*> ntt_tables;  // keyed by log_n of the twiddle table
+};
+
+struct h2a_bases {
+    const uint8_t* d = nullptr;  // n * 64 bytes, device
+    size_t n = 0;
+    bool owned = false;
+};
+
+#define H2A_FAIL(ctx, code, ...)                          \
+    do {                                                  \
+        char _b[512];                                     \
+        snprintf(_b, sizeof _b, __VA_ARGS__);             \
+        (ctx)->err = _b;                                  \
+        return (code);                                    \
+    } while (0)
+
+#define H2A_CUDA(ctx, call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (call);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            char _b[512];                                                                                \
+            snprintf(_b, sizeof _b, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            (ctx)->err = _b;                                                                             \
+            return _e == cudaErrorMemoryAllocation ? H2A_ERR_OOM : H2A_ERR_CUDA;                         \
+        }                                                                                                \
+    } while (0)
+
+#define H2A_TRY(expr)             \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != H2A_OK) return _rc; \
+    } while (0)
+
+// grow-only reservation
+int h2a_reserve(h2a_ctx* ctx, DevBuf& b, size_t bytes);
+int h2a_reserve_pinned(h2a_ctx* ctx, size_t bytes);
+
+// profiling helpers: phase_begin() resets, phase_mark() records an event after a phase
+void h2a_prof_begin(h2a_ctx* ctx, int kind);
+void h2a_prof_mark(h2a_ctx* ctx);
+void h2a_prof_end(h2a_ctx* ctx);
+
+#define H2A_LAUNCH_CHECK(ctx)                  \
+    do {                                       \
+        (ctx)->launches++;                     \
+        H2A_CUDA(ctx, cudaGetLastError());     \
+    } while (0)
+
+// implemented in msm.cu / ntt.cu / misc.cu
+int h2a_msm_run(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]);

@@ -1,0 +1,334 @@
+// msm.cu — Pippenger G1 multi-scalar multiplication for sm_100a.
+//
+// Computes the value of halo2 `arithmetic::best_multiexp(coeffs, bases)` — reached from the
+// reference through `commit_lagrange` (examples/simple-example.rs:638-640) and every commitment of
+// `create_proof` (:606-613, :702-709) — as a bucket method laid out for the GPU:
+//
+//   1. digits+histogram : scalars leave Montgomery form, are cut into W = ceil(254/c) signed c-bit
+//                         digits; |digit| selects one of 2^(c-1) buckets per window; count per bucket.
+//   2. scan             : exclusive prefix over the W * 2^(c-1) counters.
+//   3. scatter          : (point index | sign) written to its bucket's slice: a counting sort.
+//   4. accumulate       : one thread per bucket sums its points with XYZZ mixed additions; bases are
+//                         fetched with 128-bit loads, the next point prefetched during the current add.
+//   5. reduce           : per window, sum_b b * bucket[b] by segmented running sums.
+//   6. combine          : W window sums come back to the host; Horner with c doublings per window,
+//                         one inversion to canonical affine.
+// The arithmetic is 254-bit Montgomery on the 32-bit integer pipe (field.cuh); nothing here is
+// a dense contraction, so no tensor cores.
+#include <algorithm>
+#include <cstring>
+
+#include "ctx.hpp"
+#include "curve.cuh"
+#include "host_bn254.hpp"
+
+using namespace h2a;
+
+namespace {
+
+constexpr int SCAN_ITEMS = 8;       // per thread
+constexpr int SCAN_THREADS = 1024;  // per block
+constexpr int SCAN_CHUNK = SCAN_ITEMS * SCAN_THREADS;
+
+template <int C>
+struct Win {
+    static constexpr int W = (254 + C - 1) / C;
+    static constexpr uint32_t B = 1u << (C - 1);
+};
+
+// Signed-digit recoding of a canonical 254-bit scalar: digit_w in (-2^(c-1), 2^(c-1)], carries
+// ripple upward; the top window never overflows because 254 - (W-1)c <= c-1 for every c in 3..24.
+template <int C, class F>
+__device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], F f) {
+    constexpr int W = Win<C>::W;
+    constexpr uint32_t B = Win<C>::B;
+    uint32_t carry = 0;
+#pragma unroll
+    for (int w = 0; w < W; w++) {
+        const int off = w * C, i = off >> 5, sh = off & 31;
+        uint32_t v = s[i] >> sh;
+        if (sh + C > 32 && i + 1 < 8) v |= s[i + 1] << (32 - sh);
+        v &= (1u << C) - 1u;
+        v += carry;
+        const bool neg = v > B;
+        carry = neg ? 1u : 0u;
+        const uint32_t mag = neg ? (2u * B - v) : v;
+        if (mag) f(w, mag - 1u, neg);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) msm_hist_kernel(const uint8_t* __restrict__ scalars, uint32_t n,
+                                                       uint32_t* __restrict__ hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = Fr::load(scalars + 32ull * i).from_mont();
+    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(uint32_t)w * Win<C>::B + b], 1u); });
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint8_t* __restrict__ scalars, uint32_t n,
+                                                          uint32_t* __restrict__ cursor,
+                                                          uint32_t* __restrict__ sorted) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = Fr::load(scalars + 32ull * i).from_mont();
+    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool neg) {
+        uint32_t pos = atomicAdd(&cursor[(uint32_t)w * Win<C>::B + b], 1u);
+        sorted[pos] = i | (neg ? 0x80000000u : 0u);
+    });
+}
+
+// ---- exclusive scan of `n` uint32 counters, in place: three small kernels
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+        uint32_t winc = ws;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        warp_sums[lane] = winc - ws;  // exclusive
+        if (lane == 31 && total) *total = winc;
+    }
+    __syncthreads();
+    uint32_t r = inc - v + warp_sums[wid];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t* __restrict__ data, uint32_t n,
+                                                                       uint32_t* __restrict__ block_sums) {
+    uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? data[base + k] : 0;
+    __shared__ uint32_t total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint32_t* __restrict__ block_sums, uint32_t nblocks) {
+    // single block; loops if there are more than SCAN_THREADS block sums
+    __shared__ uint32_t total;
+    uint32_t running = 0;
+    for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nblocks ? block_sums[i] : 0;
+        uint32_t ex = block_exclusive_scan(v, &total);
+        if (i < nblocks) block_sums[i] = running + ex;
+        running += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __restrict__ data, uint32_t n,
+                                                                  const uint32_t* __restrict__ block_sums) {
+    uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? data[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) data[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+// ---- bucket accumulation: one thread per bucket; windows are visited top-down so the (fuller)
+// top window's buckets are scheduled first.  After the scatter, ends[k] is the end of bucket k's slice.
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __restrict__ bases,
+                                                             const uint32_t* __restrict__ sorted,
+                                                             const uint32_t* __restrict__ ends, uint32_t n_windows,
+                                                             uint32_t buckets_per_window,
+                                                             uint8_t* __restrict__ buckets_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_windows * buckets_per_window) return;
+    uint32_t w = n_windows - 1 - t / buckets_per_window;
+    uint32_t k = w * buckets_per_window + t % buckets_per_window;
+    uint32_t j = k ? ends[k - 1] : 0u, end = ends[k];
+    XYZZ acc = XYZZ::identity();
+    if (j < end) {
+        uint32_t e = sorted[j];
+        Affine p = Affine::load(bases + 64ull * (e & 0x7fffffffu));
+        for (;;) {
+            ++j;
+            uint32_t e_next = 0;
+            Affine p_next;
+            const bool more = j < end;
+            if (more) {
+                e_next = sorted[j];
+                p_next = Affine::load(bases + 64ull * (e_next & 0x7fffffffu));
+            }
+            if (!p.is_identity()) acc.add_affine(p, (e >> 31) != 0);
+            if (!more) break;
+            e = e_next;
+            p = p_next;
+        }
+    }
+    acc.store(buckets_out + 128ull * k);
+}
+
+__device__ __noinline__ void xyzz_add_nl(XYZZ& a, const XYZZ& b) { a.add(b); }
+
+// ---- segment reduction: segment `seg` of window `w` covers buckets [lo, lo+L) (0-based; bucket t
+// weighs t+1).  out = sum_t (t+1) * bucket[t] = (running-sum result) + lo * (plain sum).
+__global__ void __launch_bounds__(64) msm_reduce_segments_kernel(const uint8_t* __restrict__ buckets,
+                                                                 uint32_t n_windows, uint32_t buckets_per_window,
+                                                                 uint32_t seg_len, uint8_t* __restrict__ seg_out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t segs = buckets_per_window / seg_len;
+    if (t >= n_windows * segs) return;
+    uint32_t w = t / segs, seg = t % segs, lo = seg * seg_len;
+    const uint8_t* bp = buckets + 128ull * ((size_t)w * buckets_per_window + lo);
+    XYZZ run = XYZZ::identity(), acc = XYZZ::identity();
+    for (int i = (int)seg_len - 1; i >= 0; i--) {
+        XYZZ b = XYZZ::load(bp + 128ull * i);
+        xyzz_add_nl(run, b);
+        xyzz_add_nl(acc, run);
+    }
+    if (lo != 0 && !run.is_identity()) {  // acc += lo * run  (double-and-add, lo < 2^24)
+        XYZZ m = XYZZ::identity();
+        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
+            m = m.dbl();
+            if ((lo >> bit) & 1) xyzz_add_nl(m, run);
+        }
+        xyzz_add_nl(acc, m);
+    }
+    acc.store(seg_out + 128ull * t);
+}
+
+// ---- per-window sum of segment results: one block per window, tree in shared memory
+constexpr int WIN_THREADS = 128;
+__global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8_t* __restrict__ seg_in, uint32_t segs,
+                                                                     uint8_t* __restrict__ win_out) {
+    __shared__ __align__(16) uint8_t sh[WIN_THREADS * 128];
+    uint32_t w = blockIdx.x;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t s = threadIdx.x; s < segs; s += WIN_THREADS) {
+        XYZZ b = XYZZ::load(seg_in + 128ull * ((size_t)w * segs + s));
+        xyzz_add_nl(acc, b);
+    }
+    acc.store(sh + 128 * threadIdx.x);
+    __syncthreads();
+    for (int stride = WIN_THREADS / 2; stride > 0; stride >>= 1) {
+        if ((int)threadIdx.x < stride) {
+            XYZZ a = XYZZ::load(sh + 128 * threadIdx.x), b = XYZZ::load(sh + 128 * (threadIdx.x + stride));
+            xyzz_add_nl(a, b);
+            a.store(sh + 128 * threadIdx.x);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) XYZZ::load(sh).store(win_out + 128ull * w);
+}
+
+int pick_window(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg - 6;
+    return std::max(6, std::min(16, c));
+}
+
+template <int C>
+int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]) {
+    constexpr int W = Win<C>::W;
+    constexpr uint32_t B = Win<C>::B;
+    const uint32_t nb = (uint32_t)W * B;
+    const uint32_t seg_len = std::max(1u, std::min(32u, B / 32u));
+    const uint32_t segs = B / seg_len;
+    const uint32_t scan_blocks = (nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    cudaStream_t st = ctx->stream;
+
+    H2A_TRY(h2a_reserve(ctx, ctx->offsets, (size_t)nb * 4));
+    H2A_TRY(h2a_reserve(ctx, ctx->misc, (size_t)scan_blocks * 4 + 64));
+    H2A_TRY(h2a_reserve(ctx, ctx->sorted, n * (size_t)W * 4));
+    H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)nb * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)W * segs * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->winsums, (size_t)W * 128));
+    H2A_TRY(h2a_reserve_pinned(ctx, (size_t)W * 128));
+    uint32_t* offsets = (uint32_t*)ctx->offsets.p;
+    uint32_t* block_sums = (uint32_t*)ctx->misc.p;
+    uint32_t* sorted = (uint32_t*)ctx->sorted.p;
+
+    h2a_prof_begin(ctx, 0);
+    H2A_CUDA(ctx, cudaMemsetAsync(offsets, 0, (size_t)nb * 4, st));
+    const uint32_t pt_blocks = (uint32_t)((n + 255) / 256);
+    msm_hist_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, block_sums);
+    H2A_LAUNCH_CHECK(ctx);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, scan_blocks);
+    H2A_LAUNCH_CHECK(ctx);
+    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, block_sums);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    msm_scatter_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets, sorted);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    msm_accumulate_kernel<<<(nb + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, W, B, (uint8_t*)ctx->buckets.p);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    msm_reduce_segments_kernel<<<(W * segs + 63) / 64, 64, 0, st>>>((const uint8_t*)ctx->buckets.p, W, B, seg_len,
+                                                                   (uint8_t*)ctx->segsums.p);
+    H2A_LAUNCH_CHECK(ctx);
+    msm_window_sum_kernel<<<W, WIN_THREADS, 0, st>>>((const uint8_t*)ctx->segsums.p, segs, (uint8_t*)ctx->winsums.p);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->winsums.p, (size_t)W * 128, cudaMemcpyDeviceToHost, st));
+    H2A_CUDA(ctx, cudaStreamSynchronize(st));
+
+    // Horner over the window sums on the host: acc = acc * 2^c + S_w, top window first.
+    using namespace h2a_host;
+    const uint8_t* ws = (const uint8_t*)ctx->pinned;
+    PointX acc = px_identity();
+    for (int w = W - 1; w >= 0; w--) {
+        for (int i = 0; i < C; i++) acc = px_dbl(acc);
+        acc = px_add(acc, px_load(ws + 128 * w));
+    }
+    affine_store(out_affine, px_to_affine(acc));
+    h2a_prof_mark(ctx);
+    h2a_prof_end(ctx);
+    return H2A_OK;
+}
+
+}  // namespace
+
+int h2a_msm_run(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]) {
+    if (n == 0) {
+        memset(out_affine, 0, 64);
+        return H2A_OK;
+    }
+    if (n > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n);
+    int c = ctx->msm_window_override ? ctx->msm_window_override : pick_window(n);
+    switch (c) {
+#define H2A_CASE(C) \
+    case C:         \
+        return msm_run_c<C>(ctx, d_bases, d_scalars, n, out_affine);
+        H2A_CASE(6) H2A_CASE(7) H2A_CASE(8) H2A_CASE(9) H2A_CASE(10) H2A_CASE(11) H2A_CASE(12) H2A_CASE(13)
+        H2A_CASE(14) H2A_CASE(15) H2A_CASE(16) H2A_CASE(17) H2A_CASE(18) H2A_CASE(19) H2A_CASE(20)
+#undef H2A_CASE
+        default:
+            H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: window width %d not in 6..20", c);
+    }
+}
+
+const char* h2a_msm_phase_name(int i) {
+    static const char* names[] = {"digits+histogram", "scan", "scatter", "accumulate", "reduce", "d2h+combine"};
+    return (i >= 0 && i < 6) ? names[i] : "";
+}

@@ -1,0 +1,168 @@
+/* h2agg.h — C ABI of libh2agg.so: the B200 (sm_100a) implementation of the data-parallel hot path
+ * of halo2-aggregation: BN254 G1 MSM, Fr NTT / coset FFT / domain extension, and the batched
+ * verifier (GWC multi-open) accumulation.
+ *
+ * The reference has no FFI of its own: it is generic Rust calling the `halo2` dependency
+ * (Cargo.toml:12).  Each entry point below names the dependency function whose call it replaces
+ * and the line of the reference through which that call is reached.  INTEGRATION.md shows the Rust
+ * `extern "C"` block and the shim a maintainer adds to `halo2::arithmetic` / `halo2::poly`.
+ *
+ * Conventions
+ *  - Status: 0 = ok, negative = error; h2a_last_error(ctx) returns a message.  No aborts, no
+ *    exceptions cross the boundary.  There is no CPU fallback: without a usable CUDA device
+ *    h2a_init fails and every other call fails with H2A_ERR_NO_DEVICE.
+ *  - Field elements: 32 bytes, 4 x u64 little-endian limbs, Montgomery form (R = 2^256) — the
+ *    in-memory form of `bn256::Fr` / `bn256::Fq`, so a Rust `&[Fr]` is passed as `*const u8`.
+ *  - G1 affine points: 64 bytes x || y (each as above); the identity is 64 zero bytes.
+ *  - Results are canonical: an MSM returns the affine form of the unique group element, so any
+ *    two correct implementations agree bit for bit.
+ *  - `*_dev` variants take device pointers (inputs already resident in HBM); all others take host
+ *    pointers and do their own host<->device copies.
+ *  - A ctx is bound to one GPU and serialises its calls on one CUDA stream; use one ctx per GPU
+ *    (one process per GPU under torchrun) and distinct ctxs from distinct threads.
+ */
+#ifndef H2AGG_H
+#define H2AGG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H2A_OK 0
+#define H2A_ERR_INVALID (-1)   /* bad argument (NULL, size mismatch, log_n out of range, ...) */
+#define H2A_ERR_CUDA (-2)      /* a CUDA runtime call failed; see h2a_last_error */
+#define H2A_ERR_NO_DEVICE (-3) /* no CUDA device / wrong architecture */
+#define H2A_ERR_OOM (-4)       /* device or host allocation failed */
+#define H2A_ERR_PROOF (-5)     /* malformed proof bytes in the verifier glue */
+
+typedef struct h2a_ctx h2a_ctx;
+typedef struct h2a_bases h2a_bases;
+
+/* ---- lifecycle ------------------------------------------------------------------------- */
+int h2a_version(void);
+int h2a_device_count(void);
+/* Create a context on CUDA device `device`. */
+int h2a_init(h2a_ctx** out, int device);
+int h2a_destroy(h2a_ctx* ctx);
+const char* h2a_last_error(const h2a_ctx* ctx);
+/* The cudaStream_t all work of this ctx is launched on (for event timing by the caller). */
+void* h2a_stream(h2a_ctx* ctx);
+/* Block until everything queued on the ctx stream has finished. */
+int h2a_sync(h2a_ctx* ctx);
+/* Device memory helpers so a host program needs no other CUDA binding. */
+int h2a_dev_alloc(h2a_ctx* ctx, size_t bytes, void** out_dev);
+int h2a_dev_free(h2a_ctx* ctx, void* dev);
+int h2a_copy_h2d(h2a_ctx* ctx, void* dev, const void* host, size_t bytes);
+int h2a_copy_d2h(h2a_ctx* ctx, void* host, const void* dev, size_t bytes);
+
+/* ---- G1 MSM ----------------------------------------------------------------------------
+ * Replaces halo2 `arithmetic::best_multiexp(coeffs, bases)` as reached through
+ * `Params::commit_lagrange` / `Params::commit` (examples/simple-example.rs:638-640 and every
+ * commitment inside `create_proof`, :606-613, :702-709).
+ * Bases (`Params.g`, `Params.g_lagrange`) are uploaded once and stay resident. */
+int h2a_bases_upload(h2a_ctx* ctx, const uint8_t* affine_xy, size_t n, h2a_bases** out);
+/* Wrap bases that already live in device memory (no copy; caller keeps ownership of d_affine). */
+int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_bases** out);
+int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases);
+size_t h2a_bases_len(const h2a_bases* bases);
+
+/* out_affine = sum_{i<n} scalars[i] * bases[offset + i] */
+int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
+               uint8_t out_affine[64]);
+int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
+                   uint8_t out_affine[64]);
+/* m scalar vectors (columns) over the same bases: out_affine[j] = MSM(scalars[j][0..n[j]), bases[0..n[j])) */
+int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,
+                     uint8_t* out_affine /* m*64 */);
+/* One-shot MSM over caller-supplied host bases (verifier-side sums; Params not involved). */
+int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* scalars, size_t n,
+                     uint8_t out_affine[64]);
+/* Sum of m affine points on the host (combines per-GPU partial MSM results after the allgather). */
+int h2a_g1_sum(const uint8_t* points_affine, size_t m, uint8_t out_affine[64]);
+/* Force the Pippenger window width (0 = automatic).  For tuning and tests. */
+int h2a_msm_set_window(h2a_ctx* ctx, int c);
+
+/* ---- Fr NTT ------------------------------------------------------------------------------
+ * Replaces halo2 `arithmetic::best_fft(a, omega, log_n)` and the `EvaluationDomain` methods
+ * built on it (`lagrange_to_coeff`, `coeff_to_extended`, `extended_to_coeff`); the reference
+ * touches the domain at src/verifier.rs:252 (get_omega) and :431 (get_quotient_poly_degree).
+ * Natural order in, natural order out: a[i] <- sum_j a[j] * omega^(i*j).
+ *   inverse != 0 : omega is the FORWARD root; the transform uses omega^-1 and scales by 1/n.
+ *   coset_shift  : NULL, or g such that
+ *                  forward: a[j] is multiplied by g^j before the transform  (evaluate on g*<omega>)
+ *                  inverse: result[j] is multiplied by g^-j after the transform. */
+int h2a_ntt(h2a_ctx* ctx, uint8_t* a, uint32_t log_n, const uint8_t omega[32], int inverse,
+            const uint8_t* coset_shift);
+int h2a_ntt_dev(h2a_ctx* ctx, void* d_a, uint32_t log_n, const uint8_t omega[32], int inverse,
+                const uint8_t* coset_shift);
+/* coeff_to_extended: 2^k coefficients -> 2^ext_k evaluations on the coset g*<omega_ext>
+ * (zero padded, omega_ext = ROOT_OF_UNITY^(2^(28-ext_k))). */
+int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint32_t ext_k,
+                          const uint8_t coset_shift[32], uint8_t* out /* 2^ext_k * 32 */);
+/* extended_to_coeff: 2^ext_k coset evaluations -> 2^ext_k coefficients (caller truncates). In place. */
+int h2a_extended_to_coeff(h2a_ctx* ctx, uint8_t* ext, uint32_t ext_k, const uint8_t coset_shift[32]);
+/* omega_k = ROOT_OF_UNITY^(2^(28-k)), Montgomery form (EvaluationDomain::get_omega). */
+int h2a_fr_root_of_unity(uint32_t k, uint8_t out[32]);
+
+/* ---- verifier glue -------------------------------------------------------------------------
+ * Replaces the native values computed by `MultiopenChip::calc_witness`
+ * (src/multiopen.rs:271-509) with ONE batched device MSM per output point:
+ *   queries are grouped by rotation in ascending order, insertion order kept inside a set
+ *   (src/multiopen.rs:19-45); with S sets, m_i queries in set i, z_i = x * omega^rot_i:
+ *     W  = sum_i u^(S-1-i) W_i          ZW = sum_i u^(S-1-i) z_i W_i
+ *     F  = sum_i u^(S-1-i) sum_j v^(m_i-1-j) C_ij
+ *     E  = -(sum_i u^(S-1-i) sum_j v^(m_i-1-j) eval_ij) * G1
+ * out_efwzw = e || f || w || zw (affine), the order of the `[G1Affine; 4]` the reference packs into
+ * public inputs (examples/simple-example.rs:668-671, src/verifier.rs:739-742).
+ * Returns H2A_ERR_INVALID when n_ws differs from the number of distinct rotations. */
+int h2a_verify_accumulate(h2a_ctx* ctx, const uint8_t* commitments /* nq*64 */, const int32_t* rotations /* nq */,
+                          const uint8_t* evals /* nq*32 */, size_t nq, const uint8_t* ws /* n_ws*64 */, size_t n_ws,
+                          const uint8_t x[32], const uint8_t u[32], const uint8_t v[32], const uint8_t omega[32],
+                          const uint8_t g1[64], uint8_t out_efwzw[256]);
+/* Batch of independent proofs (BASELINE config 5): proof p uses queries [q_off[p], q_off[p+1]) and
+ * witnesses [w_off[p], w_off[p+1]); xuv = n_proofs * (x||u||v).  All 4*n_proofs sums share one launch. */
+int h2a_verify_accumulate_batch(h2a_ctx* ctx, size_t n_proofs, const uint8_t* commitments, const int32_t* rotations,
+                                const uint8_t* evals, const size_t* q_off, const uint8_t* ws, const size_t* w_off,
+                                const uint8_t* xuv, const uint8_t omega[32], const uint8_t g1[64],
+                                uint8_t* out_efwzw /* n_proofs*256 */);
+/* H = sum_i (x^n)^i h_i  (src/vanishing.rs:177-188) as one device MSM. */
+int h2a_fold_h(h2a_ctx* ctx, const uint8_t* h_pieces /* m*64 */, size_t m, const uint8_t xn[32], uint8_t out_affine[64]);
+
+/* Blake2b transcript with Challenge255 (src/transcript.rs:58,72,105-107,122-124). */
+typedef struct h2a_transcript h2a_transcript;
+h2a_transcript* h2a_transcript_new(void);
+void h2a_transcript_free(h2a_transcript* t);
+int h2a_transcript_common_point(h2a_transcript* t, const uint8_t point_affine[64]);
+int h2a_transcript_common_scalar(h2a_transcript* t, const uint8_t scalar[32]);
+int h2a_transcript_squeeze_challenge(h2a_transcript* t, uint8_t out_scalar[32]);
+
+/* ---- synthetic inputs for benchmarks (written straight into device memory) -----------------
+ * Counter-based and position-addressable: element i depends only on (seed, first + i).
+ * Scalars are uniform in [0, r); bases are uniform curve points found by try-and-increment
+ * (x from the stream, y = sqrt(x^3 + 3), sign from the stream). */
+int h2a_gen_scalars_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out /* n*32 */);
+int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out /* n*64 */);
+
+/* ---- test / measurement hooks ---------------------------------------------------------- */
+/* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inv 5 neg. */
+int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
+int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* Per-phase device times of the most recent MSM / NTT on this ctx, measured with CUDA events on the
+ * ctx stream.  Enable with h2a_set_profiling(ctx, 1).  Returns the number of phases written (<= cap). */
+int h2a_set_profiling(h2a_ctx* ctx, int on);
+int h2a_last_phase_ms(h2a_ctx* ctx, float* ms, int cap);
+const char* h2a_phase_name(int phase_kind /* 0 msm, 1 ntt */, int index);
+/* Number of kernels this library has launched on the ctx since creation. */
+uint64_t h2a_launch_count(const h2a_ctx* ctx);
+/* Integer-pipe micro-benchmark: dependent-free IMAD chains; returns achieved 10^12 IMAD thread-instructions/s. */
+int h2a_bench_imad(h2a_ctx* ctx, double* out_tera_imad_per_s);
+/* Field-multiply micro-benchmark: returns 10^9 Fq Montgomery products per second. */
+int h2a_bench_modmul(h2a_ctx* ctx, double* out_giga_mul_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H2AGG_H */

@@ -1,0 +1,72 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol include/h2agg.h declares,
+refuses to run without a GPU (no fallback), and its host-side glue (transcript, point sums, roots of
+unity) agrees with the oracle.  No device compute here."""
+import random
+
+import numpy as np
+import pytest
+
+import halo2_aggregation_b200 as h2a
+from oracle import pymodel as pm
+
+
+def test_library_exports_every_declared_symbol():
+    lib = h2a.load_library()
+    syms = h2a.declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert lib.h2a_version() == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(h2a.H2AError) as e:
+        h2a.Context(0)
+    assert e.value.code == -3
+    assert h2a.load_library().h2a_device_count() == 0
+
+
+def test_root_of_unity_matches_oracle(orc):
+    for k in (0, 1, 9, 20, 23, 28):
+        assert bytes(h2a.fr_root_of_unity(k)) == bytes(orc.fr_root_of_unity(k))
+    with pytest.raises(h2a.H2AError):
+        h2a.fr_root_of_unity(29)
+
+
+def test_transcript_matches_oracle_and_pymodel(orc):
+    rng = random.Random(99)
+    t, o, m = h2a.Transcript(), orc.Transcript(), pm.Blake2bTranscript()
+    for _ in range(60):
+        kind = rng.randrange(3)
+        if kind == 0:
+            pt = pm.g1_mul(pm.G1, rng.randrange(1, pm.R))
+            b = np.frombuffer(pm.affine_bytes(pt), dtype=np.uint8)
+            t.common_point(b); o.common_point(b); m.common_point(pt)
+        elif kind == 1:
+            s = rng.randrange(pm.R)
+            b = np.frombuffer(pm.fr_mont_bytes(s), dtype=np.uint8)
+            t.common_scalar(b); o.common_scalar(b); m.common_scalar(s)
+        else:
+            got = t.squeeze_challenge()
+            assert bytes(got) == bytes(o.squeeze())
+            assert pm.fr_from_mont_bytes(got) == m.squeeze_challenge()
+    with pytest.raises(h2a.H2AError):
+        t.common_point(np.zeros(64, np.uint8))  # the identity cannot be absorbed
+
+
+def test_g1_sum_matches_oracle(orc):
+    pts = orc.gen_bases(3, 9)
+    acc = np.zeros(64, np.uint8)
+    for i in range(9):
+        acc = orc.g1_add(acc, pts[64 * i:64 * i + 64])
+    assert bytes(h2a.g1_sum(pts)) == bytes(acc)
+    # P + (-P) + O
+    p = pm.g1_mul(pm.G1, 5)
+    trio = np.frombuffer(pm.affine_bytes(p) + pm.affine_bytes(pm.g1_neg(p)) + bytes(64), dtype=np.uint8)
+    assert bytes(h2a.g1_sum(trio)) == bytes(64)
+    dbl = np.frombuffer(pm.affine_bytes(p) * 2, dtype=np.uint8)
+    assert pm.affine_from_bytes(h2a.g1_sum(dbl)) == pm.g1_mul(pm.G1, 10)
+    assert bytes(h2a.g1_sum(np.zeros(0, np.uint8))) == bytes(64)
