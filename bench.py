@@ -227,7 +227,7 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         names = [p[0] for p in phases[0]]
         avg = {nm: sum(ph[i][1] for ph in phases) / len(phases) for i, nm in enumerate(names)}
-        acc_ms = avg.get("accumulate", 0.0)
+        acc_ms = avg.get("accumulate+merge", 0.0)
         imad_peak = ctx.bench_imad()
         modmul_rate = ctx.bench_modmul()
         c = 16 if args.log_n >= 22 else max(6, min(16, args.log_n - 6))

@@ -21,3 +21,4 @@ from .api import (  # noqa: F401
     g1_sum,
     fr_root_of_unity,
 )
+from .dist import allgather_points, allgather_sum, shard_range  # noqa: F401

@@ -6,10 +6,14 @@
 //
 //   1. digits+histogram : scalars leave Montgomery form, are cut into W = ceil(254/c) signed c-bit
 //                         digits; |digit| selects one of 2^(c-1) buckets per window; count per bucket.
-//   2. scan             : exclusive prefix over the W * 2^(c-1) counters.
+//   2. scan             : exclusive prefix over the W * 2^(c-1) counters; in the same pass every bucket is
+//                         cut into tasks of at most L entries (a second prefix) so that no thread ever
+//                         owns more than L additions, however skewed the scalars are.
 //   3. scatter          : (point index | sign) written to its bucket's slice: a counting sort.
-//   4. accumulate       : one thread per bucket sums its points with XYZZ mixed additions; bases are
+//   4. accumulate       : one thread per task sums its points with XYZZ mixed additions; bases are
 //                         fetched with 128-bit loads, the next point prefetched during the current add.
+//   4b. merge           : buckets that were cut into several tasks are folded by one warp each
+//                         (lanes stride over the partial sums, then a shuffle tree).
 //   5. reduce           : per window, sum_b b * bucket[b] by segmented running sums.
 //   6. combine          : W window sums come back to the host; Horner with c doublings per window,
 //                         one inversion to canonical affine.
@@ -79,89 +83,113 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint8_t* __restr
     });
 }
 
-// ---- exclusive scan of `n` uint32 counters, in place: three small kernels
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t warp_sums[32];
+// ---- exclusive scan over the bucket counters, in place, carried together with a second prefix:
+// tasks(k) = ceil(count(k) / L).  Both ride in one 64-bit value (low word: entries, high word: tasks).
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* total) {
+    __shared__ uint64_t warp_sums[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t inc = v;
+    uint64_t inc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+        uint64_t t = __shfl_up_sync(0xffffffffu, inc, d);
         if (lane >= d) inc += t;
     }
     if (lane == 31) warp_sums[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
-        uint32_t winc = ws;
+        uint64_t ws = (lane < (int)(blockDim.x >> 5)) ? warp_sums[lane] : 0;
+        uint64_t winc = ws;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+            uint64_t t = __shfl_up_sync(0xffffffffu, winc, d);
             if (lane >= d) winc += t;
         }
         warp_sums[lane] = winc - ws;  // exclusive
         if (lane == 31 && total) *total = winc;
     }
     __syncthreads();
-    uint32_t r = inc - v + warp_sums[wid];
+    uint64_t r = inc - v + warp_sums[wid];
     __syncthreads();
     return r;
 }
+__device__ __forceinline__ uint64_t pack_count(uint32_t cnt, uint32_t task_len) {
+    return (uint64_t)cnt | ((uint64_t)((cnt + task_len - 1) / task_len) << 32);
+}
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t* __restrict__ data, uint32_t n,
-                                                                       uint32_t* __restrict__ block_sums) {
+                                                                       uint32_t task_len,
+                                                                       uint64_t* __restrict__ block_sums) {
     uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-    uint32_t s = 0;
+    uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? data[base + k] : 0;
-    __shared__ uint32_t total;
+    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? pack_count(data[base + k], task_len) : 0;
+    __shared__ uint64_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint32_t* __restrict__ block_sums, uint32_t nblocks) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint64_t* __restrict__ block_sums, uint32_t nblocks) {
     // single block; loops if there are more than SCAN_THREADS block sums
-    __shared__ uint32_t total;
-    uint32_t running = 0;
+    __shared__ uint64_t total;
+    uint64_t running = 0;
     for (uint32_t base = 0; base < nblocks; base += SCAN_THREADS) {
         uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nblocks ? block_sums[i] : 0;
-        uint32_t ex = block_exclusive_scan(v, &total);
+        uint64_t v = i < nblocks ? block_sums[i] : 0;
+        uint64_t ex = block_exclusive_scan(v, &total);
         if (i < nblocks) block_sums[i] = running + ex;
         running += total;
         __syncthreads();
     }
 }
 
+// data[k] <- start of bucket k; task_off[k] <- first task of bucket k (task_off[n] = number of tasks);
+// buckets cut into more than one task are appended to multi_list.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __restrict__ data, uint32_t n,
-                                                                  const uint32_t* __restrict__ block_sums) {
+                                                                  uint32_t task_len,
+                                                                  const uint64_t* __restrict__ block_sums,
+                                                                  uint32_t* __restrict__ task_off,
+                                                                  uint32_t* __restrict__ multi_list,
+                                                                  uint32_t* __restrict__ n_multi) {
     uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], s = 0;
+    uint64_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n) ? data[base + k] : 0;
+        v[k] = (base + k < n) ? pack_count(data[base + k], task_len) : 0;
         s += v[k];
     }
-    uint32_t ex = block_exclusive_scan(s, nullptr) + block_sums[blockIdx.x];
+    uint64_t ex = block_exclusive_scan(s, nullptr) + block_sums[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < n) data[base + k] = ex;
+        if (base + k < n) {
+            data[base + k] = (uint32_t)ex;
+            task_off[base + k] = (uint32_t)(ex >> 32);
+            if ((uint32_t)(v[k] >> 32) > 1u) multi_list[atomicAdd(n_multi, 1u)] = base + k;
+        }
         ex += v[k];
+        if (base + k == n - 1) task_off[n] = (uint32_t)(ex >> 32);
     }
 }
 
-// ---- bucket accumulation: one thread per bucket; windows are visited top-down so the (fuller)
-// top window's buckets are scheduled first.  After the scatter, ends[k] is the end of bucket k's slice.
+// ---- bucket accumulation: one thread per task (a run of at most task_len entries of one bucket).
+// Tasks are visited from the last bucket down, so the (fuller) top window is scheduled first.
+// After the scatter, ends[k] is the end of bucket k's slice.  partial[t] receives task t's sum.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __restrict__ bases,
                                                              const uint32_t* __restrict__ sorted,
-                                                             const uint32_t* __restrict__ ends, uint32_t n_windows,
-                                                             uint32_t buckets_per_window,
-                                                             uint8_t* __restrict__ buckets_out) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_windows * buckets_per_window) return;
-    uint32_t w = n_windows - 1 - t / buckets_per_window;
-    uint32_t k = w * buckets_per_window + t % buckets_per_window;
-    uint32_t j = k ? ends[k - 1] : 0u, end = ends[k];
+                                                             const uint32_t* __restrict__ ends,
+                                                             const uint32_t* __restrict__ task_off, uint32_t n_buckets,
+                                                             uint32_t task_len, uint8_t* __restrict__ partial) {
+    const uint32_t n_tasks = task_off[n_buckets];
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_tasks) return;
+    const uint32_t t = n_tasks - 1u - tid;
+    uint32_t lo = 0, hi = n_buckets;  // task_off[lo] <= t < task_off[hi]
+    while (hi - lo > 1u) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t k = lo;
+    uint32_t j = (k ? ends[k - 1] : 0u) + (t - task_off[k]) * task_len;
+    const uint32_t end = min(j + task_len, ends[k]);
     XYZZ acc = XYZZ::identity();
     if (j < end) {
         uint32_t e = sorted[j];
@@ -181,25 +209,64 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __re
             p = p_next;
         }
     }
-    acc.store(buckets_out + 128ull * k);
+    acc.store(partial + 128ull * t);
 }
 
 __device__ __noinline__ void xyzz_add_nl(XYZZ& a, const XYZZ& b) { a.add(b); }
 
+// ---- merge: a bucket that was cut into several tasks is folded by one warp; the sum replaces the
+// bucket's first partial.
+__device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int off) {
+    XYZZ r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_down_sync(0xffffffffu, v.x.l[i], off);
+        r.y.l[i] = __shfl_down_sync(0xffffffffu, v.y.l[i], off);
+        r.zz.l[i] = __shfl_down_sync(0xffffffffu, v.zz.l[i], off);
+        r.zzz.l[i] = __shfl_down_sync(0xffffffffu, v.zzz.l[i], off);
+    }
+    return r;
+}
+constexpr int MERGE_WARPS = 4;
+__global__ void __launch_bounds__(32 * MERGE_WARPS) msm_merge_kernel(const uint32_t* __restrict__ task_off,
+                                                                    const uint32_t* __restrict__ multi_list,
+                                                                    const uint32_t* __restrict__ n_multi,
+                                                                    uint8_t* __restrict__ partial) {
+    const uint32_t m = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= *n_multi) return;
+    const uint32_t k = multi_list[m], t0 = task_off[k], cnt = task_off[k + 1] - t0;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t i = lane; i < cnt; i += 32) {
+        XYZZ b = XYZZ::load(partial + 128ull * (t0 + i));
+        xyzz_add_nl(acc, b);
+    }
+    const uint32_t live = min(cnt, 32u);
+    for (int off = 16; off > 0; off >>= 1) {
+        XYZZ other = shfl_down_xyzz(acc, off);
+        if ((int)lane < off && lane + off < live) xyzz_add_nl(acc, other);
+    }
+    if (lane == 0) acc.store(partial + 128ull * t0);
+}
+
 // ---- segment reduction: segment `seg` of window `w` covers buckets [lo, lo+L) (0-based; bucket t
 // weighs t+1).  out = sum_t (t+1) * bucket[t] = (running-sum result) + lo * (plain sum).
-__global__ void __launch_bounds__(64) msm_reduce_segments_kernel(const uint8_t* __restrict__ buckets,
+// Bucket k's value is partial[task_off[k]] (identity when the bucket has no task).
+__global__ void __launch_bounds__(64) msm_reduce_segments_kernel(const uint8_t* __restrict__ partial,
+                                                                 const uint32_t* __restrict__ task_off,
                                                                  uint32_t n_windows, uint32_t buckets_per_window,
                                                                  uint32_t seg_len, uint8_t* __restrict__ seg_out) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t segs = buckets_per_window / seg_len;
     if (t >= n_windows * segs) return;
     uint32_t w = t / segs, seg = t % segs, lo = seg * seg_len;
-    const uint8_t* bp = buckets + 128ull * ((size_t)w * buckets_per_window + lo);
+    const uint32_t k0 = w * buckets_per_window + lo;
     XYZZ run = XYZZ::identity(), acc = XYZZ::identity();
     for (int i = (int)seg_len - 1; i >= 0; i--) {
-        XYZZ b = XYZZ::load(bp + 128ull * i);
-        xyzz_add_nl(run, b);
+        const uint32_t t0 = task_off[k0 + i], t1 = task_off[k0 + i + 1];
+        if (t1 > t0) {
+            XYZZ b = XYZZ::load(partial + 128ull * t0);
+            xyzz_add_nl(run, b);
+        }
         xyzz_add_nl(acc, run);
     }
     if (lo != 0 && !run.is_identity()) {  // acc += lo * run  (double-and-add, lo < 2^24)
@@ -249,43 +316,59 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, si
     constexpr int W = Win<C>::W;
     constexpr uint32_t B = Win<C>::B;
     const uint32_t nb = (uint32_t)W * B;
+    if ((uint64_t)n * W >= (1ull << 32)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
     const uint32_t seg_len = std::max(1u, std::min(32u, B / 32u));
     const uint32_t segs = B / seg_len;
     const uint32_t scan_blocks = (nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    // task length: at most four times the mean bucket load (uniformly distributed digits then give one task
+    // per bucket), and short enough that about 2^18 tasks exist to fill 148 SMs when n is small
+    const uint32_t task_len = (uint32_t)std::max<uint64_t>(
+        32, std::min<uint64_t>(std::max<uint64_t>(256, 4 * (n >> (C - 1))), ((uint64_t)n * W) >> 18));
+    const uint32_t max_multi = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / task_len + 1);
+    const uint32_t max_tasks = nb + (uint32_t)((uint64_t)n * W / task_len) + 1;
     cudaStream_t st = ctx->stream;
 
     H2A_TRY(h2a_reserve(ctx, ctx->offsets, (size_t)nb * 4));
-    H2A_TRY(h2a_reserve(ctx, ctx->misc, (size_t)scan_blocks * 4 + 64));
+    H2A_TRY(h2a_reserve(ctx, ctx->cursor, ((size_t)nb + 1) * 4));                    // task_off
+    H2A_TRY(h2a_reserve(ctx, ctx->misc, (size_t)scan_blocks * 8 + 64));              // block sums + n_multi
+    H2A_TRY(h2a_reserve(ctx, ctx->heavy, ((size_t)max_multi + 1) * 4));              // multi_list
     H2A_TRY(h2a_reserve(ctx, ctx->sorted, n * (size_t)W * 4));
-    H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)nb * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)max_tasks * 128));                // per-task partial sums
     H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)W * segs * 128));
     H2A_TRY(h2a_reserve(ctx, ctx->winsums, (size_t)W * 128));
     H2A_TRY(h2a_reserve_pinned(ctx, (size_t)W * 128));
     uint32_t* offsets = (uint32_t*)ctx->offsets.p;
-    uint32_t* block_sums = (uint32_t*)ctx->misc.p;
+    uint32_t* task_off = (uint32_t*)ctx->cursor.p;
+    uint64_t* block_sums = (uint64_t*)ctx->misc.p;
+    uint32_t* n_multi = (uint32_t*)((uint8_t*)ctx->misc.p + (size_t)scan_blocks * 8);
+    uint32_t* multi_list = (uint32_t*)ctx->heavy.p;
     uint32_t* sorted = (uint32_t*)ctx->sorted.p;
+    uint8_t* partial = (uint8_t*)ctx->buckets.p;
 
     h2a_prof_begin(ctx, 0);
     H2A_CUDA(ctx, cudaMemsetAsync(offsets, 0, (size_t)nb * 4, st));
+    H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 4, st));
     const uint32_t pt_blocks = (uint32_t)((n + 255) / 256);
     msm_hist_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, block_sums);
+    scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums);
     H2A_LAUNCH_CHECK(ctx);
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, scan_blocks);
     H2A_LAUNCH_CHECK(ctx);
-    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, block_sums);
+    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums, task_off, multi_list, n_multi);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
     msm_scatter_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets, sorted);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_accumulate_kernel<<<(nb + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, W, B, (uint8_t*)ctx->buckets.p);
+    msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, partial);
+    H2A_LAUNCH_CHECK(ctx);
+    msm_merge_kernel<<<(max_multi + MERGE_WARPS - 1) / MERGE_WARPS, 32 * MERGE_WARPS, 0, st>>>(task_off, multi_list, n_multi,
+                                                                                             partial);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_reduce_segments_kernel<<<(W * segs + 63) / 64, 64, 0, st>>>((const uint8_t*)ctx->buckets.p, W, B, seg_len,
-                                                                   (uint8_t*)ctx->segsums.p);
+    msm_reduce_segments_kernel<<<(W * segs + 63) / 64, 64, 0, st>>>(partial, task_off, W, B, seg_len, (uint8_t*)ctx->segsums.p);
     H2A_LAUNCH_CHECK(ctx);
     msm_window_sum_kernel<<<W, WIN_THREADS, 0, st>>>((const uint8_t*)ctx->segsums.p, segs, (uint8_t*)ctx->winsums.p);
     H2A_LAUNCH_CHECK(ctx);
@@ -329,6 +412,6 @@ int h2a_msm_run(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, 
 }
 
 const char* h2a_msm_phase_name(int i) {
-    static const char* names[] = {"digits+histogram", "scan", "scatter", "accumulate", "reduce", "d2h+combine"};
+    static const char* names[] = {"digits+histogram", "scan", "scatter", "accumulate+merge", "reduce", "d2h+combine"};
     return (i >= 0 && i < 6) ? names[i] : "";
 }

@@ -167,6 +167,29 @@ def test_msm_adversarial_inputs(ctx, orc):
     hb.free(); hr.free()
 
 
+def test_msm_skewed_scalars_large(ctx, orc):
+    """Heavy buckets: every point in one bucket / two buckets / a 17-bit range (witness-like columns)."""
+    n = 1 << 17
+    bases = orc.gen_bases(55, n)
+    hb = ctx.upload_bases(bases)
+    rng = random.Random(3)
+    cases = {
+        "all_ones": np.frombuffer(pm.fr_mont_bytes(1) * n, dtype=np.uint8),
+        "all_same_big": np.frombuffer(pm.fr_mont_bytes(R - 12345) * n, dtype=np.uint8),
+        "bits": orc.to_mont(1, ints_to_bytes([rng.getrandbits(1) for _ in range(n)])),
+        "limbs17": orc.to_mont(1, ints_to_bytes([rng.getrandbits(17) for _ in range(n)])),
+        "mostly_zero": orc.to_mont(1, ints_to_bytes([rng.randrange(R) if i % 64 == 0 else 0 for i in range(n)])),
+    }
+    for name, sm in cases.items():
+        assert bytes(ctx.msm(hb, sm)) == bytes(orc.msm(bases, sm)), name
+    for c in (8, 12, 14):     # window widths whose top window holds only a few bits
+        ctx.set_msm_window(c)
+        sm = orc.gen_scalars(56, n)
+        assert bytes(ctx.msm(hb, sm)) == bytes(orc.msm(bases, sm)), c
+    ctx.set_msm_window(0)
+    hb.free()
+
+
 def test_msm_batch_and_dev(ctx, orc):
     n = 5000
     bases = orc.gen_bases(31, n)

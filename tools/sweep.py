@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Sweeps of BASELINE configs 1 and 2 on one GPU: G1 MSM 2^16..2^24 and Fr NTT k=16..24, inputs
+resident in HBM, timed with CUDA events on the library stream.  One JSON line per size."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import halo2_aggregation_b200 as h2a
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--msm", default="16,18,20,22,24")
+    ap.add_argument("--ntt", default="16,18,20,22,24")
+    ap.add_argument("--windows", default="")
+    ap.add_argument("--reps", type=int, default=5)
+    args = ap.parse_args()
+    ctx = h2a.Context(0)
+    ctx.set_profiling(True)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def timeit(fn, reps):
+        for _ in range(2):
+            fn()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    msm_sizes = [int(x) for x in args.msm.split(",") if x]
+    if msm_sizes:
+        nmax = 1 << max(msm_sizes)
+        db = torch.empty(64 * nmax, dtype=torch.uint8, device="cuda")
+        ds = torch.empty(32 * nmax, dtype=torch.uint8, device="cuda")
+        ctx.gen_bases_dev(1, nmax, db.data_ptr())
+        ctx.gen_scalars_dev(2, nmax, ds.data_ptr())
+        hb = ctx.bases_from_device(db.data_ptr(), nmax)
+        for lg in msm_sizes:
+            n = 1 << lg
+            wins = [int(x) for x in args.windows.split(",") if x] or [0]
+            for c in wins:
+                ctx.set_msm_window(c)
+                ms = timeit(lambda: ctx.msm_dev(hb, ds.data_ptr(), n), args.reps)
+                print(json.dumps({"op": "msm_g1", "log_n": lg, "window": c, "ms": ms, "mpts_per_s": n / ms / 1e3,
+                                  "phases_ms": dict(ctx.last_phases(0))}), flush=True)
+            ctx.set_msm_window(0)
+        hb.free()
+        del db, ds
+    for k in [int(x) for x in args.ntt.split(",") if x]:
+        n = 1 << k
+        d = torch.empty(32 * n, dtype=torch.uint8, device="cuda")
+        ctx.gen_scalars_dev(3, n, d.data_ptr())
+        w = h2a.fr_root_of_unity(k)
+        ms = timeit(lambda: ctx.ntt_dev(d.data_ptr(), k, w), args.reps)
+        ph = dict(ctx.last_phases(1))
+        kern_ms = sum(ph.values())
+        print(json.dumps({"op": "ntt_fr", "log_n": k, "ms": ms, "kernel_ms": kern_ms, "melem_per_s": n / ms / 1e3,
+                          "algo_gbs": 64 * n / (kern_ms * 1e-3) / 1e9, "phases_ms": ph}), flush=True)
+        del d
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
