@@ -308,6 +308,11 @@ class Bases:
     def __len__(self):
         return int(self.ctx.lib.h2a_bases_len(self.h))
 
+    def precompute(self, window_bits=-1):
+        """Build the window tables 2^(window_bits*w) * P_i (h2a_bases_precompute); 0 drops them."""
+        self.ctx._check(self.ctx.lib.h2a_bases_precompute(self.ctx.h, self.h, int(window_bits)))
+        return self
+
     def free(self):
         if self.h:
             self.ctx._check(self.ctx.lib.h2a_bases_free(self.ctx.h, self.h))

@@ -50,14 +50,24 @@ int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_b
 }
 int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases) {
     if (!ctx || !bases) return H2A_ERR_INVALID;
-    if (bases->owned && bases->d) {
-        H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        H2A_CUDA(ctx, cudaFree((void*)bases->d));
-    }
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bases->table) H2A_CUDA(ctx, cudaFree(bases->table));
+    if (bases->owned && bases->d) H2A_CUDA(ctx, cudaFree((void*)bases->d));
     delete bases;
     return H2A_OK;
 }
 size_t h2a_bases_len(const h2a_bases* bases) { return bases ? bases->n : 0; }
+int h2a_bases_precompute(h2a_ctx* ctx, h2a_bases* bases, int window_bits) {
+    if (!ctx || !bases) return H2A_ERR_INVALID;
+    if (window_bits == 0) {  // drop the tables
+        H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (bases->table) H2A_CUDA(ctx, cudaFree(bases->table));
+        bases->table = nullptr;
+        bases->table_c = 0;
+        return H2A_OK;
+    }
+    return h2a_msm_precompute(ctx, bases, window_bits);
+}
 
 // ------------------------------------------------------------------ MSM
 int h2a_msm_set_window(h2a_ctx* ctx, int c) {
@@ -71,7 +81,7 @@ int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const vo
     if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;
     if (offset > bases->n || n > bases->n - offset)
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
-    return h2a_msm_run(ctx, bases->d + 64 * offset, (const uint8_t*)d_scalars, n, out_affine);
+    return h2a_msm_run(ctx, bases, offset, (const uint8_t*)d_scalars, n, out_affine);
 }
 
 int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
@@ -85,7 +95,7 @@ int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_
     }
     H2A_TRY(h2a_reserve(ctx, ctx->scalars, n * 32));
     H2A_CUDA(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
-    return h2a_msm_run(ctx, bases->d + 64 * offset, (const uint8_t*)ctx->scalars.p, n, out_affine);
+    return h2a_msm_run(ctx, bases, offset, (const uint8_t*)ctx->scalars.p, n, out_affine);
 }
 
 int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,

@@ -48,6 +48,8 @@ struct h2a_bases {
     const uint8_t* d = nullptr;  // n * 64 bytes, device
     size_t n = 0;
     bool owned = false;
+    uint8_t* table = nullptr;  // optional precomputed window tables T[w][i] = 2^(c*w) P_i, W * n * 64 bytes
+    int table_c = 0;
 };
 
 #define H2A_FAIL(ctx, code, ...)                          \
@@ -91,4 +93,6 @@ void h2a_prof_end(h2a_ctx* ctx);
     } while (0)
 
 // implemented in msm.cu / ntt.cu / misc.cu
-int h2a_msm_run(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]);
+int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n,
+                uint8_t out_affine[64]);
+int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c);

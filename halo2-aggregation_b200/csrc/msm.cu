@@ -12,8 +12,8 @@
 //   3. scatter          : (point index | sign) written to its bucket's slice: a counting sort.
 //   4. accumulate       : one thread per task sums its points with XYZZ mixed additions; bases are
 //                         fetched with 128-bit loads, the next point prefetched during the current add.
-//   4b. merge           : buckets that were cut into several tasks are folded by one warp each
-//                         (lanes stride over the partial sums, then a shuffle tree).
+//   4b. merge           : buckets that were cut into several tasks are folded by one thread each (up to 32
+//                         tasks) or one warp each (lanes stride over the partial sums, then a shuffle tree).
 //   5. reduce           : per window, sum_b b * bucket[b] by segmented running sums.
 //   6. combine          : W window sums come back to the host; Horner with c doublings per window,
 //                         one inversion to canonical affine.
@@ -61,26 +61,69 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], F f) {
     }
 }
 
-template <int C>
+// PRE = the bases carry precomputed window tables T[w][i] = 2^(c*w) * P_i: every window then feeds the
+// same 2^(c-1) buckets and an entry names the table element (w * stride + first + i) instead of i.
+template <int C, bool PRE>
 __global__ void __launch_bounds__(256) msm_hist_kernel(const uint8_t* __restrict__ scalars, uint32_t n,
                                                        uint32_t* __restrict__ hist) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = Fr::load(scalars + 32ull * i).from_mont();
-    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool) { atomicAdd(&hist[(uint32_t)w * Win<C>::B + b], 1u); });
+    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool) { atomicAdd(&hist[PRE ? b : (uint32_t)w * Win<C>::B + b], 1u); });
 }
 
-template <int C>
+template <int C, bool PRE>
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint8_t* __restrict__ scalars, uint32_t n,
+                                                          uint32_t stride, uint32_t first,
                                                           uint32_t* __restrict__ cursor,
                                                           uint32_t* __restrict__ sorted) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = Fr::load(scalars + 32ull * i).from_mont();
     for_each_digit<C>(s.l, [&](int w, uint32_t b, bool neg) {
-        uint32_t pos = atomicAdd(&cursor[(uint32_t)w * Win<C>::B + b], 1u);
-        sorted[pos] = i | (neg ? 0x80000000u : 0u);
+        uint32_t pos = atomicAdd(&cursor[PRE ? b : (uint32_t)w * Win<C>::B + b], 1u);
+        uint32_t idx = PRE ? (uint32_t)w * stride + first + i : i;
+        sorted[pos] = idx | (neg ? 0x80000000u : 0u);
     });
+}
+
+// Builds the window tables: thread i walks P_i -> 2^c P_i -> 2^(2c) P_i ... in XYZZ (X, Y parked in the
+// destination slots), then normalises all W-1 multiples with ONE field inversion (Montgomery's trick over
+// the thread's own chain).  The per-window ZZ, ZZZ and prefix products live in local memory by design.
+constexpr int MAX_PRE_WINDOWS = 24;
+__global__ void __launch_bounds__(128) msm_precompute_kernel(const uint8_t* __restrict__ bases, uint32_t n, int c,
+                                                             int n_windows, uint8_t* __restrict__ table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine p = Affine::load(bases + 64ull * i);
+    p.store(table + 64ull * i);
+    if (p.is_identity()) {
+        for (int w = 1; w < n_windows; w++) p.store(table + 64ull * ((size_t)w * n + i));
+        return;
+    }
+    Fq zz[MAX_PRE_WINDOWS], zzz[MAX_PRE_WINDOWS], pre[MAX_PRE_WINDOWS];
+    XYZZ cur = XYZZ::from_affine(p);
+    Fq run = Fq::one();
+    for (int w = 1; w < n_windows; w++) {
+        for (int k = 0; k < c; k++) cur = cur.dbl();
+        uint8_t* slot = table + 64ull * ((size_t)w * n + i);
+        cur.x.store(slot);
+        cur.y.store(slot + 32);
+        zz[w] = cur.zz;
+        zzz[w] = cur.zzz;
+        run = run * cur.zzz;
+        pre[w] = run;
+    }
+    Fq inv = run.inv();  // 1 / (zzz_1 ... zzz_{W-1}); a point of prime order never doubles to the identity
+    for (int w = n_windows - 1; w >= 1; w--) {
+        Fq zi = (w > 1) ? inv * pre[w - 1] : inv;  // 1 / zzz_w
+        inv = inv * zzz[w];
+        Fq zzi = (zi * zz[w]).sqr();               // 1 / zz_w  (zz^3 = zzz^2)
+        uint8_t* slot = table + 64ull * ((size_t)w * n + i);
+        Fq x = Fq::load(slot) * zzi, y = Fq::load(slot + 32) * zi;
+        x.store(slot);
+        y.store(slot + 32);
+    }
 }
 
 // ---- exclusive scan over the bucket counters, in place, carried together with a second prefix:
@@ -148,7 +191,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __re
                                                                   uint32_t task_len,
                                                                   const uint64_t* __restrict__ block_sums,
                                                                   uint32_t* __restrict__ task_off,
-                                                                  uint32_t* __restrict__ multi_list,
+                                                                  uint32_t* __restrict__ multi_list, uint32_t multi_cap,
                                                                   uint32_t* __restrict__ n_multi) {
     uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     uint64_t v[SCAN_ITEMS], s = 0;
@@ -163,7 +206,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __re
         if (base + k < n) {
             data[base + k] = (uint32_t)ex;
             task_off[base + k] = (uint32_t)(ex >> 32);
-            if ((uint32_t)(v[k] >> 32) > 1u) multi_list[atomicAdd(n_multi, 1u)] = base + k;
+            const uint32_t nt = (uint32_t)(v[k] >> 32);
+            // buckets cut into 2..32 tasks are merged by one thread each (list grows up from 0),
+            // heavier ones by one warp each (list grows down from the end)
+            if (nt > 32u) multi_list[multi_cap - 1u - atomicAdd(n_multi + 1, 1u)] = base + k;
+            else if (nt > 1u) multi_list[atomicAdd(n_multi, 1u)] = base + k;
         }
         ex += v[k];
         if (base + k == n - 1) task_off[n] = (uint32_t)(ex >> 32);
@@ -171,17 +218,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __re
 }
 
 // ---- bucket accumulation: one thread per task (a run of at most task_len entries of one bucket).
-// Tasks are visited from the last bucket down, so the (fuller) top window is scheduled first.
+// The fuller buckets are scheduled first: the top window's (last) when every window has its own buckets,
+// the lowest-numbered ones when precomputed tables fold all windows into one bucket set.
 // After the scatter, ends[k] is the end of bucket k's slice.  partial[t] receives task t's sum.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __restrict__ bases,
                                                              const uint32_t* __restrict__ sorted,
                                                              const uint32_t* __restrict__ ends,
                                                              const uint32_t* __restrict__ task_off, uint32_t n_buckets,
-                                                             uint32_t task_len, uint8_t* __restrict__ partial) {
+                                                             uint32_t task_len, bool top_down,
+                                                             uint8_t* __restrict__ partial) {
     const uint32_t n_tasks = task_off[n_buckets];
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n_tasks) return;
-    const uint32_t t = n_tasks - 1u - tid;
+    const uint32_t t = top_down ? n_tasks - 1u - tid : tid;
     uint32_t lo = 0, hi = n_buckets;  // task_off[lo] <= t < task_off[hi]
     while (hi - lo > 1u) {
         uint32_t mid = (lo + hi) >> 1;
@@ -228,24 +277,38 @@ __device__ __forceinline__ XYZZ shfl_down_xyzz(const XYZZ& v, int off) {
     return r;
 }
 constexpr int MERGE_WARPS = 4;
-__global__ void __launch_bounds__(32 * MERGE_WARPS) msm_merge_kernel(const uint32_t* __restrict__ task_off,
-                                                                    const uint32_t* __restrict__ multi_list,
-                                                                    const uint32_t* __restrict__ n_multi,
-                                                                    uint8_t* __restrict__ partial) {
+__global__ void __launch_bounds__(32 * MERGE_WARPS) msm_merge_heavy_kernel(const uint32_t* __restrict__ task_off,
+                                                                          const uint32_t* __restrict__ multi_list,
+                                                                          uint32_t multi_cap,
+                                                                          const uint32_t* __restrict__ n_multi,
+                                                                          uint8_t* __restrict__ partial) {
     const uint32_t m = blockIdx.x * MERGE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (m >= *n_multi) return;
-    const uint32_t k = multi_list[m], t0 = task_off[k], cnt = task_off[k + 1] - t0;
+    if (m >= n_multi[1]) return;
+    const uint32_t k = multi_list[multi_cap - 1u - m], t0 = task_off[k], cnt = task_off[k + 1] - t0;
     XYZZ acc = XYZZ::identity();
     for (uint32_t i = lane; i < cnt; i += 32) {
         XYZZ b = XYZZ::load(partial + 128ull * (t0 + i));
         xyzz_add_nl(acc, b);
     }
-    const uint32_t live = min(cnt, 32u);
     for (int off = 16; off > 0; off >>= 1) {
         XYZZ other = shfl_down_xyzz(acc, off);
-        if ((int)lane < off && lane + off < live) xyzz_add_nl(acc, other);
+        if ((int)lane < off) xyzz_add_nl(acc, other);
     }
     if (lane == 0) acc.store(partial + 128ull * t0);
+}
+__global__ void __launch_bounds__(128) msm_merge_light_kernel(const uint32_t* __restrict__ task_off,
+                                                              const uint32_t* __restrict__ multi_list,
+                                                              const uint32_t* __restrict__ n_multi,
+                                                              uint8_t* __restrict__ partial) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_multi[0]) return;
+    const uint32_t k = multi_list[m], t0 = task_off[k], cnt = task_off[k + 1] - t0;
+    XYZZ acc = XYZZ::load(partial + 128ull * t0);
+    for (uint32_t i = 1; i < cnt; i++) {
+        XYZZ b = XYZZ::load(partial + 128ull * (t0 + i));
+        xyzz_add_nl(acc, b);
+    }
+    acc.store(partial + 128ull * t0);
 }
 
 // ---- segment reduction: segment `seg` of window `w` covers buckets [lo, lo+L) (0-based; bucket t
@@ -282,6 +345,8 @@ __global__ void __launch_bounds__(64) msm_reduce_segments_kernel(const uint8_t* 
 
 // ---- per-window sum of segment results: one block per window, tree in shared memory
 constexpr int WIN_THREADS = 128;
+// (a "window" here is a group of `segs` consecutive segment sums: one Pippenger window, or a slice of the
+// single shared window when the bases carry precomputed tables)
 __global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8_t* __restrict__ seg_in, uint32_t segs,
                                                                      uint8_t* __restrict__ win_out) {
     __shared__ __align__(16) uint8_t sh[WIN_THREADS * 128];
@@ -304,27 +369,39 @@ __global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8
     if (threadIdx.x == 0) XYZZ::load(sh).store(win_out + 128ull * w);
 }
 
-int pick_window(size_t n) {
+int pick_window(size_t n) {  // from the measured sweep (tools/sweep.py --windows ...), B200
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    int c = lg - 6;
-    return std::max(6, std::min(16, c));
+    if (lg >= 19) return 16;
+    if (lg >= 17) return 15;
+    if (lg >= 14) return 10;
+    return std::max(6, std::min(10, lg - 4));
 }
 
-template <int C>
-int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]) {
+template <int C, bool PRE>
+int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t first, const uint8_t* d_scalars, size_t n,
+              uint8_t out_affine[64]) {
     constexpr int W = Win<C>::W;
     constexpr uint32_t B = Win<C>::B;
-    const uint32_t nb = (uint32_t)W * B;
-    if ((uint64_t)n * W >= (1ull << 32)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
+    constexpr int BW = PRE ? 1 : W;  // windows of buckets
+    const uint32_t nb = (uint32_t)BW * B;
+    if ((uint64_t)n * W >= (1ull << 32) || (PRE && (uint64_t)stride * W >= (1ull << 31)))
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
     const uint32_t seg_len = std::max(1u, std::min(32u, B / 32u));
     const uint32_t segs = B / seg_len;
+    // groups of segment sums returned to the host: one per window, or (PRE) 64 slices of the single window
+    const uint32_t groups = PRE ? std::min(64u, segs) : (uint32_t)W;
+    const uint32_t segs_per_group = (uint32_t)BW * segs / groups;
     const uint32_t scan_blocks = (nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    // task length: at most four times the mean bucket load (uniformly distributed digits then give one task
-    // per bucket), and short enough that about 2^18 tasks exist to fill 148 SMs when n is small
-    const uint32_t task_len = (uint32_t)std::max<uint64_t>(
-        32, std::min<uint64_t>(std::max<uint64_t>(256, 4 * (n >> (C - 1))), ((uint64_t)n * W) >> 18));
+    // task length: twice the mean bucket load (uniformly distributed digits then give one task per bucket while
+    // the fuller buckets fed by a narrow top window are cut into a few equal tasks), shorter when buckets are scarce
+    // so that about 2^17 tasks exist to fill 148 SMs
+    const uint64_t mean_load = ((uint64_t)n * W) / nb;
+    uint64_t task_len64 = std::max<uint64_t>(128, 2 * mean_load);
+    if (nb < (1u << 17)) task_len64 = std::max<uint64_t>(32, std::min<uint64_t>(task_len64, ((uint64_t)n * W) >> 17));
+    const uint32_t task_len = (uint32_t)task_len64;
     const uint32_t max_multi = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / task_len + 1);
+    const uint32_t max_heavy = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / (32ull * task_len) + 1);
     const uint32_t max_tasks = nb + (uint32_t)((uint64_t)n * W / task_len) + 1;
     cudaStream_t st = ctx->stream;
 
@@ -334,9 +411,9 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, si
     H2A_TRY(h2a_reserve(ctx, ctx->heavy, ((size_t)max_multi + 1) * 4));              // multi_list
     H2A_TRY(h2a_reserve(ctx, ctx->sorted, n * (size_t)W * 4));
     H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)max_tasks * 128));                // per-task partial sums
-    H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)W * segs * 128));
-    H2A_TRY(h2a_reserve(ctx, ctx->winsums, (size_t)W * 128));
-    H2A_TRY(h2a_reserve_pinned(ctx, (size_t)W * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)BW * segs * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->winsums, (size_t)groups * 128));
+    H2A_TRY(h2a_reserve_pinned(ctx, (size_t)groups * 128));
     uint32_t* offsets = (uint32_t*)ctx->offsets.p;
     uint32_t* task_off = (uint32_t*)ctx->cursor.p;
     uint64_t* block_sums = (uint64_t*)ctx->misc.p;
@@ -347,42 +424,49 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, si
 
     h2a_prof_begin(ctx, 0);
     H2A_CUDA(ctx, cudaMemsetAsync(offsets, 0, (size_t)nb * 4, st));
-    H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 4, st));
+    H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 8, st));
     const uint32_t pt_blocks = (uint32_t)((n + 255) / 256);
-    msm_hist_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
+    msm_hist_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
     scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums);
     H2A_LAUNCH_CHECK(ctx);
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, scan_blocks);
     H2A_LAUNCH_CHECK(ctx);
-    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums, task_off, multi_list, n_multi);
+    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums, task_off, multi_list,
+                                                            max_multi + 1, n_multi);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_scatter_kernel<C><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets, sorted);
+    msm_scatter_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, stride, first, offsets, sorted);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, partial);
+    msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, !PRE,
+                                                                       partial);
     H2A_LAUNCH_CHECK(ctx);
-    msm_merge_kernel<<<(max_multi + MERGE_WARPS - 1) / MERGE_WARPS, 32 * MERGE_WARPS, 0, st>>>(task_off, multi_list, n_multi,
-                                                                                             partial);
+    msm_merge_heavy_kernel<<<(max_heavy + MERGE_WARPS - 1) / MERGE_WARPS, 32 * MERGE_WARPS, 0, st>>>(
+        task_off, multi_list, max_multi + 1, n_multi, partial);
     H2A_LAUNCH_CHECK(ctx);
-    h2a_prof_mark(ctx);
-    msm_reduce_segments_kernel<<<(W * segs + 63) / 64, 64, 0, st>>>(partial, task_off, W, B, seg_len, (uint8_t*)ctx->segsums.p);
-    H2A_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<<<W, WIN_THREADS, 0, st>>>((const uint8_t*)ctx->segsums.p, segs, (uint8_t*)ctx->winsums.p);
+    msm_merge_light_kernel<<<(max_multi + 127) / 128, 128, 0, st>>>(task_off, multi_list, n_multi, partial);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->winsums.p, (size_t)W * 128, cudaMemcpyDeviceToHost, st));
+    msm_reduce_segments_kernel<<<(BW * segs + 63) / 64, 64, 0, st>>>(partial, task_off, BW, B, seg_len, (uint8_t*)ctx->segsums.p);
+    H2A_LAUNCH_CHECK(ctx);
+    msm_window_sum_kernel<<<groups, WIN_THREADS, 0, st>>>((const uint8_t*)ctx->segsums.p, segs_per_group, (uint8_t*)ctx->winsums.p);
+    H2A_LAUNCH_CHECK(ctx);
+    h2a_prof_mark(ctx);
+    H2A_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->winsums.p, (size_t)groups * 128, cudaMemcpyDeviceToHost, st));
     H2A_CUDA(ctx, cudaStreamSynchronize(st));
 
-    // Horner over the window sums on the host: acc = acc * 2^c + S_w, top window first.
     using namespace h2a_host;
     const uint8_t* ws = (const uint8_t*)ctx->pinned;
     PointX acc = px_identity();
-    for (int w = W - 1; w >= 0; w--) {
-        for (int i = 0; i < C; i++) acc = px_dbl(acc);
-        acc = px_add(acc, px_load(ws + 128 * w));
+    if (PRE) {  // the tables already carry the 2^(c*w) factors: plain sum of the slices
+        for (uint32_t g = 0; g < groups; g++) acc = px_add(acc, px_load(ws + 128 * g));
+    } else {    // Horner over the window sums: acc = acc * 2^c + S_w, top window first
+        for (int w = W - 1; w >= 0; w--) {
+            for (int i = 0; i < C; i++) acc = px_dbl(acc);
+            acc = px_add(acc, px_load(ws + 128 * w));
+        }
     }
     affine_store(out_affine, px_to_affine(acc));
     h2a_prof_mark(ctx);
@@ -392,23 +476,53 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, si
 
 }  // namespace
 
-int h2a_msm_run(h2a_ctx* ctx, const uint8_t* d_bases, const uint8_t* d_scalars, size_t n, uint8_t out_affine[64]) {
+int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n,
+                uint8_t out_affine[64]) {
     if (n == 0) {
         memset(out_affine, 0, 64);
         return H2A_OK;
     }
     if (n > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n);
-    int c = ctx->msm_window_override ? ctx->msm_window_override : pick_window(n);
+    const bool pre = bases->table != nullptr && (ctx->msm_window_override == 0 || ctx->msm_window_override == bases->table_c);
+    int c = pre ? bases->table_c : (ctx->msm_window_override ? ctx->msm_window_override : pick_window(n));
     switch (c) {
-#define H2A_CASE(C) \
-    case C:         \
-        return msm_run_c<C>(ctx, d_bases, d_scalars, n, out_affine);
+#define H2A_CASE(C)                                                                                                     \
+    case C:                                                                                                             \
+        return pre ? msm_run_c<C, true>(ctx, bases->table, (uint32_t)bases->n, (uint32_t)offset, d_scalars, n, out_affine) \
+                   : msm_run_c<C, false>(ctx, bases->d + 64 * offset, 0, 0, d_scalars, n, out_affine);
         H2A_CASE(6) H2A_CASE(7) H2A_CASE(8) H2A_CASE(9) H2A_CASE(10) H2A_CASE(11) H2A_CASE(12) H2A_CASE(13)
         H2A_CASE(14) H2A_CASE(15) H2A_CASE(16) H2A_CASE(17) H2A_CASE(18) H2A_CASE(19) H2A_CASE(20)
 #undef H2A_CASE
         default:
             H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: window width %d not in 6..20", c);
     }
+}
+
+// Builds T[w][i] = 2^(c*w) * P_i for w < ceil(254/c) next to the bases (W * n * 64 bytes of HBM).
+int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c) {
+    if (c < 0) c = bases->n >= (1u << 21) ? 20 : 16;  // automatic choice from the measured sweep
+    if (c < 11 || c > 20) H2A_FAIL(ctx, H2A_ERR_INVALID, "precompute: window width %d not in 11..20", c);
+    const int W = (254 + c - 1) / c;
+    if ((uint64_t)bases->n * W >= (1ull << 31)) H2A_FAIL(ctx, H2A_ERR_INVALID, "precompute: %zu bases x %d windows too large", bases->n, W);
+    if (bases->table) {
+        H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        H2A_CUDA(ctx, cudaFree(bases->table));
+        bases->table = nullptr;
+    }
+    if (bases->n == 0) return H2A_OK;
+    void* t = nullptr;
+    H2A_CUDA(ctx, cudaMalloc(&t, (size_t)W * bases->n * 64));
+    msm_precompute_kernel<<<(unsigned)((bases->n + 127) / 128), 128, 0, ctx->stream>>>(bases->d, (uint32_t)bases->n, c, W, (uint8_t*)t);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(t);
+        H2A_FAIL(ctx, H2A_ERR_CUDA, "precompute: %s", cudaGetErrorString(e));
+    }
+    bases->table = (uint8_t*)t;
+    bases->table_c = c;
+    return H2A_OK;
 }
 
 const char* h2a_msm_phase_name(int i) {

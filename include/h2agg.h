@@ -67,6 +67,11 @@ int h2a_bases_upload(h2a_ctx* ctx, const uint8_t* affine_xy, size_t n, h2a_bases
 int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_bases** out);
 int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases);
 size_t h2a_bases_len(const h2a_bases* bases);
+/* Optional, once per bases handle: build window tables T[w][i] = 2^(window_bits*w) * P_i next to the bases
+ * (ceil(254/window_bits) * n * 64 bytes of HBM; window_bits in 11..20, -1 = automatic, 0 drops the tables).  Every later MSM
+ * over this handle then needs ceil(254/window_bits) additions per point into ONE shared bucket set instead of
+ * one bucket set per window.  The result of an MSM is unchanged (same group element, bit for bit). */
+int h2a_bases_precompute(h2a_ctx* ctx, h2a_bases* bases, int window_bits);
 
 /* out_affine = sum_{i<n} scalars[i] * bases[offset + i] */
 int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,

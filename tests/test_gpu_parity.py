@@ -190,6 +190,37 @@ def test_msm_skewed_scalars_large(ctx, orc):
     hb.free()
 
 
+@pytest.mark.parametrize("c", [11, 13, 16, 20])
+def test_msm_precomputed_tables(ctx, orc, c):
+    """h2a_bases_precompute: same group element, bit for bit, for every kind of input."""
+    n = 6000
+    bases = orc.gen_bases(61, n).copy()
+    bases[64 * 17:64 * 18] = 0                                   # an identity base
+    bases[64 * 30:64 * 31] = bases[64 * 29:64 * 30]              # a repeated base
+    hb = ctx.upload_bases(bases).precompute(c)
+    rng = random.Random(c)
+    cases = {
+        "uniform": orc.gen_scalars(62, n),
+        "ones": np.frombuffer(pm.fr_mont_bytes(1) * n, dtype=np.uint8),
+        "r_minus_1": np.frombuffer(pm.fr_mont_bytes(R - 1) * n, dtype=np.uint8),
+        "bits": orc.to_mont(1, ints_to_bytes([rng.getrandbits(1) for _ in range(n)])),
+        "zeros": np.zeros(32 * n, np.uint8),
+    }
+    for name, sm in cases.items():
+        assert bytes(ctx.msm(hb, sm)) == bytes(orc.msm(bases, sm)), name
+    sm = cases["uniform"]
+    assert bytes(ctx.msm(hb, sm[:32 * 1000], offset=2500)) == bytes(orc.msm(bases[64 * 2500:64 * 3500], sm[:32 * 1000]))
+    # an explicit different window falls back to the plain path; dropping the tables too
+    ctx.set_msm_window(9)
+    assert bytes(ctx.msm(hb, sm)) == bytes(orc.msm(bases, sm))
+    ctx.set_msm_window(0)
+    hb.precompute(0)
+    assert bytes(ctx.msm(hb, sm)) == bytes(orc.msm(bases, sm))
+    with pytest.raises(h2a.H2AError):
+        hb.precompute(25)
+    hb.free()
+
+
 def test_msm_batch_and_dev(ctx, orc):
     n = 5000
     bases = orc.gen_bases(31, n)
@@ -222,6 +253,10 @@ def test_msm_linearity_at_bench_size(ctx):
     ctx.set_msm_window(14)
     assert bytes(ctx.msm_dev(hb, ds, n)) == bytes(full)
     ctx.set_msm_window(0)
+    # precomputed window tables (the benchmark configuration) give the same element
+    hb.precompute(20)
+    assert bytes(ctx.msm_dev(hb, ds, n)) == bytes(full)
+    assert bytes(ctx.msm_dev(hb, ds + 32 * half, half, offset=half)) == bytes(hi)
     m = 1 << 16
     ones = np.frombuffer(pm.fr_mont_bytes(1) * m, dtype=np.uint8)
     pts = ctx.d2h(db, 64 * m)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--ntt", default="16,18,20,22,24")
     ap.add_argument("--windows", default="")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--precompute", default="", help="comma list of table window widths to time as well")
     args = ap.parse_args()
     ctx = h2a.Context(0)
     ctx.set_profiling(True)
@@ -55,6 +56,16 @@ def main():
                 print(json.dumps({"op": "msm_g1", "log_n": lg, "window": c, "ms": ms, "mpts_per_s": n / ms / 1e3,
                                   "phases_ms": dict(ctx.last_phases(0))}), flush=True)
             ctx.set_msm_window(0)
+        for c in [int(x) for x in args.precompute.split(",") if x]:
+            for lg in msm_sizes:
+                n = 1 << lg
+                hp = ctx.bases_from_device(db.data_ptr(), n)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream); hp.precompute(c); e1.record(stream); ctx.sync(); torch.cuda.synchronize()
+                ms = timeit(lambda: ctx.msm_dev(hp, ds.data_ptr(), n), args.reps)
+                print(json.dumps({"op": "msm_g1_precomputed", "log_n": lg, "window": c, "ms": ms, "mpts_per_s": n / ms / 1e3,
+                                  "precompute_ms": e0.elapsed_time(e1), "phases_ms": dict(ctx.last_phases(0))}), flush=True)
+                hp.free()
         hb.free()
         del db, ds
     for k in [int(x) for x in args.ntt.split(",") if x]:
