@@ -10,6 +10,8 @@ without a B200 raises.
 from .api import (  # noqa: F401
     Context,
     Bases,
+    Circuit,
+    serialize_shape,
     Transcript,
     EvaluationDomain,
     H2AError,

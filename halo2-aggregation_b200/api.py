@@ -299,6 +299,83 @@ class Context:
         return out
 
 
+SHAPE_MAGIC = 0x48324153
+
+
+def serialize_shape(shape):
+    """Word stream of csrc/plonk_shape.hpp from any object with the attributes of the reference's vk-derived
+    parameters (k, bf, degree, num_*, *_queries, gates, constants, lookups, perm_columns)."""
+    w = [SHAPE_MAGIC, shape.k, shape.bf, shape.degree, shape.num_instance, shape.num_advice, shape.num_fixed]
+    for qs in (shape.advice_queries, shape.fixed_queries, shape.instance_queries):
+        w.append(len(qs))
+        for col, rot in qs:
+            w += [col, rot & 0xFFFFFFFF]
+
+    def prog(p):
+        out = [len(p)]
+        for op, arg in p:
+            out += [op, arg]
+        return out
+
+    w.append(len(shape.gates))
+    for g in shape.gates:
+        w += prog(g)
+    w.append(len(shape.constants))
+    w.append(len(shape.lookups))
+    for inputs, tables in shape.lookups:
+        w.append(len(inputs))
+        for p in inputs:
+            w += prog(p)
+        w.append(len(tables))
+        for p in tables:
+            w += prog(p)
+    w.append(len(shape.perm_columns))
+    for t, c, q in shape.perm_columns:
+        w += [t, c, q]
+    return np.array(w, dtype=np.uint32)
+
+
+class Circuit:
+    """h2a_circuit: a circuit shape + verifying key (+ proving key for `prove`)."""
+
+    def __init__(self, ctx, shape, constants_mont):
+        self.ctx = ctx
+        words = serialize_shape(shape)
+        consts = _bytes(constants_mont) if len(shape.constants) else np.zeros(0, np.uint8)
+        h = ctypes.c_void_p()
+        ctx._check(ctx.lib.h2a_circuit_create(ctx.h, _ptr(words), c_sz(words.size), _ptr(consts) if consts.size else None,
+                                              c_sz(len(shape.constants)), ctypes.byref(h)))
+        self.h = h
+        self.n_instance = shape.num_instance
+
+    def free(self):
+        if self.h:
+            self.ctx._check(self.ctx.lib.h2a_circuit_free(self.ctx.h, self.h))
+            self.h = None
+
+    def set_vk(self, fixed_commitments, sigma_commitments, vk_hash):
+        f, s = _bytes(fixed_commitments), _bytes(sigma_commitments)
+        self.ctx._check(self.ctx.lib.h2a_circuit_set_vk(self.ctx.h, self.h, _ptr(f), _ptr(s), _ptr(_bytes(vk_hash))))
+
+    def verify(self, instance_commitments, proof):
+        """(e, f, w, zw) of one proof: 256 bytes."""
+        ic = _bytes(instance_commitments)
+        pr = np.frombuffer(bytes(proof), dtype=np.uint8)
+        out = np.zeros(256, np.uint8)
+        self.ctx._check(self.ctx.lib.h2a_verify_proof(self.ctx.h, self.h, _ptr(ic), _ptr(pr), c_sz(pr.size), _ptr(out)))
+        return out
+
+    def verify_batch(self, instance_commitments, proofs):
+        ic = _bytes(instance_commitments)
+        bufs = [np.frombuffer(bytes(p), dtype=np.uint8) for p in proofs]
+        m = len(bufs)
+        ptrs = (ctypes.c_void_p * m)(*[b.ctypes.data for b in bufs])
+        lens = (c_sz * m)(*[b.size for b in bufs])
+        out = np.zeros(256 * m, np.uint8)
+        self.ctx._check(self.ctx.lib.h2a_verify_proof_batch(self.ctx.h, self.h, c_sz(m), _ptr(ic), ptrs, lens, _ptr(out)))
+        return out.reshape(m, 256)
+
+
 class Bases:
     """Device-resident affine bases (`Params.g` / `Params.g_lagrange`)."""
 

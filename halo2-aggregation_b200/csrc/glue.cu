@@ -15,6 +15,7 @@
 #include "ctx.hpp"
 #include "curve.cuh"
 #include "host_bn254.hpp"
+#include "host_glue.hpp"
 
 namespace dev {
 using namespace h2a;
@@ -105,118 +106,14 @@ int h2a_small_msm(h2a_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, co
     return H2A_OK;
 }
 
-// ====================================================================== Blake2b transcript (host)
-namespace {
-
-class Blake2bState {
-  public:
-    Blake2bState(unsigned out_len, const char personal[16]) : out_len_(out_len) {
-        static const uint64_t iv[8] = {0x6a09e667f3bcc908ull, 0xbb67ae8584caa73bull, 0x3c6ef372fe94f82bull,
-                                       0xa54ff53a5f1d36f1ull, 0x510e527fade682d1ull, 0x9b05688c2b3e6c1full,
-                                       0x1f83d9abfb41bd6bull, 0x5be0cd19137e2179ull};
-        memcpy(iv_, iv, sizeof iv);
-        memcpy(h_, iv, sizeof iv);
-        h_[0] ^= 0x01010000ull ^ out_len;  // fanout = depth = 1, no key
-        uint64_t p0, p1;
-        memcpy(&p0, personal, 8);
-        memcpy(&p1, personal + 8, 8);
-        h_[6] ^= p0;
-        h_[7] ^= p1;
-    }
-    void absorb(const uint8_t* data, size_t len) {
-        for (size_t i = 0; i < len; i++) {
-            if (fill_ == 128) {  // a full block is only compressed once more input follows it
-                counter_ += 128;
-                round_block(false);
-                fill_ = 0;
-            }
-            block_[fill_++] = data[i];
-        }
-    }
-    void digest(uint8_t* out) const {  // does not disturb the running state
-        Blake2bState c = *this;
-        c.counter_ += c.fill_;
-        memset(c.block_ + c.fill_, 0, 128 - c.fill_);
-        c.round_block(true);
-        memcpy(out, c.h_, out_len_);
-    }
-
-  private:
-    static uint64_t ror(uint64_t v, int r) { return (v >> r) | (v << (64 - r)); }
-    void round_block(bool final) {
-        static const uint8_t sigma[10][16] = {
-            {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
-            {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
-            {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
-            {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
-            {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0}};
-        uint64_t m[16], v[16];
-        memcpy(m, block_, 128);
-        for (int i = 0; i < 8; i++) {
-            v[i] = h_[i];
-            v[i + 8] = iv_[i];
-        }
-        v[12] ^= counter_;  // 64-bit byte counter is ample for a transcript
-        if (final) v[14] = ~v[14];
-        for (int r = 0; r < 12; r++) {
-            const uint8_t* s = sigma[r % 10];
-            for (int g = 0; g < 8; g++) {
-                int a, b, c, d;
-                if (g < 4) { a = g; b = 4 + g; c = 8 + g; d = 12 + g; }
-                else { a = g - 4; b = 4 + (g - 3) % 4; c = 8 + (g - 2) % 4; d = 12 + (g - 1) % 4; }
-                v[a] += v[b] + m[s[2 * g]];
-                v[d] = ror(v[d] ^ v[a], 32);
-                v[c] += v[d];
-                v[b] = ror(v[b] ^ v[c], 24);
-                v[a] += v[b] + m[s[2 * g + 1]];
-                v[d] = ror(v[d] ^ v[a], 16);
-                v[c] += v[d];
-                v[b] = ror(v[b] ^ v[c], 63);
-            }
-        }
-        for (int i = 0; i < 8; i++) h_[i] ^= v[i] ^ v[i + 8];
-    }
-    uint64_t h_[8], iv_[8];
-    uint8_t block_[128];
-    size_t fill_ = 0;
-    uint64_t counter_ = 0;
-    unsigned out_len_;
-};
-
-h2a_host::Fr fr_from_wide(const uint8_t b[64]) {  // 512-bit LE integer mod r -> Montgomery
-    using namespace h2a_host;
-    El lo, hi, r2;
-    memcpy(lo.v, b, 32);
-    memcpy(hi.v, b + 32, 32);
-    memcpy(r2.v, MOD_R.r2, 32);
-    El r3 = el_mul(r2, r2, MOD_R);
-    // el_mul tolerates one unreduced (< 2^256) operand: the result stays below 2r before the final subtraction
-    return Fr{el_add(el_mul(lo, r2, MOD_R), el_mul(hi, r3, MOD_R), MOD_R)};
-}
-
-}  // namespace
-
 struct h2a_transcript {
-    Blake2bState st{64, "Halo2-Transcript"};
+    h2a_glue::Transcript t;
 };
 
-// ====================================================================== verifier accumulation
-namespace {
-
-struct TermList {
-    std::vector<uint8_t> bases, scalars;
-    std::vector<uint32_t> offsets{0};
-    void term(const uint8_t* base64, const h2a_host::Fr& s) {
-        bases.insert(bases.end(), base64, base64 + 64);
-        uint8_t b[32];
-        h2a_host::fr_store(b, s);
-        scalars.insert(scalars.end(), b, b + 32);
-    }
-    void close_sum() { offsets.push_back((uint32_t)(bases.size() / 64)); }
-};
+namespace h2a_glue {
 
 // Appends the four sums (e, f, w, zw) of one proof.  Returns false if n_ws != number of rotation sets.
-bool expand_proof(TermList& tl, const uint8_t* commitments, const int32_t* rotations, const uint8_t* evals, size_t nq,
+bool expand_proof(TermList& tl, const CommitmentEmitter& emit, const int32_t* rotations, const uint8_t* evals, size_t nq,
                   const uint8_t* ws, size_t n_ws, const uint8_t* x_, const uint8_t* u_, const uint8_t* v_,
                   const h2a_host::Fr& omega, const h2a_host::Fr& omega_inv, const uint8_t* g1) {
     using namespace h2a_host;
@@ -253,7 +150,7 @@ bool expand_proof(TermList& tl, const uint8_t* commitments, const int32_t* rotat
     }
     tl.term(g1, neg(e_scalar));                                                       // E
     tl.close_sum();
-    for (auto& t : fterms) tl.term(commitments + 64 * t.q, t.s);                      // F
+    for (auto& t : fterms) emit(tl, t.q, t.s);                                        // F
     tl.close_sum();
     for (size_t i = 0; i < S; i++) tl.term(ws + 64 * i, upow[i]);                     // W
     tl.close_sum();
@@ -262,7 +159,10 @@ bool expand_proof(TermList& tl, const uint8_t* commitments, const int32_t* rotat
     return true;
 }
 
-}  // namespace
+
+}  // namespace h2a_glue
+using h2a_glue::TermList;
+using h2a_glue::expand_proof;
 
 extern "C" {
 
@@ -270,36 +170,16 @@ h2a_transcript* h2a_transcript_new(void) { return new h2a_transcript(); }
 void h2a_transcript_free(h2a_transcript* t) { delete t; }
 int h2a_transcript_common_point(h2a_transcript* t, const uint8_t point_affine[64]) {
     if (!t || !point_affine) return H2A_ERR_INVALID;
-    using namespace h2a_host;
-    PointA p = affine_load(point_affine);
-    if (is_identity(p)) return H2A_ERR_INVALID;  // halo2 cannot absorb the identity's coordinates
-    uint8_t buf[65];
-    buf[0] = 1;
-    uint64_t raw[4];
-    fq_to_raw(p.x, raw);
-    memcpy(buf + 1, raw, 32);
-    fq_to_raw(p.y, raw);
-    memcpy(buf + 33, raw, 32);
-    t->st.absorb(buf, 65);
-    return H2A_OK;
+    return t->t.common_point(h2a_host::affine_load(point_affine)) ? H2A_OK : H2A_ERR_INVALID;
 }
 int h2a_transcript_common_scalar(h2a_transcript* t, const uint8_t scalar[32]) {
     if (!t || !scalar) return H2A_ERR_INVALID;
-    uint8_t buf[33];
-    buf[0] = 2;
-    uint64_t raw[4];
-    h2a_host::fr_to_raw(h2a_host::fr_load(scalar), raw);
-    memcpy(buf + 1, raw, 32);
-    t->st.absorb(buf, 33);
+    t->t.common_scalar(h2a_host::fr_load(scalar));
     return H2A_OK;
 }
 int h2a_transcript_squeeze_challenge(h2a_transcript* t, uint8_t out_scalar[32]) {
     if (!t || !out_scalar) return H2A_ERR_INVALID;
-    uint8_t zero = 0;
-    t->st.absorb(&zero, 1);
-    uint8_t wide[64];
-    t->st.digest(wide);
-    h2a_host::fr_store(out_scalar, fr_from_wide(wide));
+    h2a_host::fr_store(out_scalar, t->t.squeeze());
     return H2A_OK;
 }
 
@@ -314,7 +194,9 @@ int h2a_verify_accumulate_batch(h2a_ctx* ctx, size_t n_proofs, const uint8_t* co
     for (size_t p = 0; p < n_proofs; p++) {
         size_t q0 = q_off[p], q1 = q_off[p + 1], w0 = w_off[p], w1 = w_off[p + 1];
         if (q1 < q0 || w1 < w0) H2A_FAIL(ctx, H2A_ERR_INVALID, "verify_accumulate: offsets of proof %zu not monotone", p);
-        if (!expand_proof(tl, commitments + 64 * q0, rotations + q0, evals + 32 * q0, q1 - q0, ws + 64 * w0, w1 - w0,
+        const uint8_t* cbase = commitments + 64 * q0;
+        h2a_glue::CommitmentEmitter emit = [cbase](TermList& t, size_t q, const Fr& sc) { t.term(cbase + 64 * q, sc); };
+        if (!expand_proof(tl, emit, rotations + q0, evals + 32 * q0, q1 - q0, ws + 64 * w0, w1 - w0,
                           xuv + 96 * p, xuv + 96 * p + 32, xuv + 96 * p + 64, om, om_inv, g1))
             H2A_FAIL(ctx, H2A_ERR_INVALID, "verify_accumulate: proof %zu has %zu W points for a different number of rotation sets",
                      p, w1 - w0);

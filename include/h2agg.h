@@ -135,6 +135,30 @@ int h2a_verify_accumulate_batch(h2a_ctx* ctx, size_t n_proofs, const uint8_t* co
 /* H = sum_i (x^n)^i h_i  (src/vanishing.rs:177-188) as one device MSM. */
 int h2a_fold_h(h2a_ctx* ctx, const uint8_t* h_pieces /* m*64 */, size_t m, const uint8_t xn[32], uint8_t out_affine[64]);
 
+/* ---- whole-proof verifier glue ------------------------------------------------------------------
+ * Replaces the native side of `VerifierChip::_verify_proof` (src/verifier.rs:286-762): given the circuit
+ * description the reference takes from the verifying key (:286-311), the vk commitments and the proof
+ * bytes, replay the Blake2b transcript in the reference's wire order (:341-510), recompute the challenges
+ * (theta, beta, gamma, y, x, v, u), l_0/l_last/l_blind (:513-591), the gate / permutation / lookup
+ * expressions and the expected h(x) (src/vanishing.rs:145-175), assemble the query list (:654-715) and
+ * evaluate (e, f, w, zw) for ALL proofs of a batch in one device launch.
+ * `shape_words`: see csrc/plonk_shape.hpp for the word stream.  `vk_hash`: the transcript scalar derived
+ * from `format!("{:?}", vk.pinned())` (src/verifier.rs:341-358) — an input, since the dependency's Debug
+ * output cannot be reproduced outside it.  Proof encoding: 32-byte compressed points (x little-endian,
+ * bit 255 = parity of y, identity = zeros) and 32-byte little-endian canonical scalars.
+ * H2A_ERR_PROOF: truncated / trailing bytes, a point not on the curve, a non-canonical scalar. */
+typedef struct h2a_circuit h2a_circuit;
+int h2a_circuit_create(h2a_ctx* ctx, const uint32_t* shape_words, size_t n_words, const uint8_t* constants /* n*32 */,
+                       size_t n_constants, h2a_circuit** out);
+int h2a_circuit_free(h2a_ctx* ctx, h2a_circuit* circuit);
+int h2a_circuit_set_vk(h2a_ctx* ctx, h2a_circuit* circuit, const uint8_t* fixed_commitments /* n_fixed*64 */,
+                       const uint8_t* sigma_commitments /* n_perm*64 */, const uint8_t vk_hash[32]);
+int h2a_verify_proof(h2a_ctx* ctx, const h2a_circuit* circuit, const uint8_t* instance_commitments /* n_instance*64 */,
+                     const uint8_t* proof, size_t proof_len, uint8_t out_efwzw[256]);
+int h2a_verify_proof_batch(h2a_ctx* ctx, const h2a_circuit* circuit, size_t n_proofs,
+                           const uint8_t* instance_commitments /* n_proofs*n_instance*64 */, const uint8_t* const* proofs,
+                           const size_t* proof_lens, uint8_t* out_efwzw /* n_proofs*256 */);
+
 /* Blake2b transcript with Challenge255 (src/transcript.rs:58,72,105-107,122-124). */
 typedef struct h2a_transcript h2a_transcript;
 h2a_transcript* h2a_transcript_new(void);

@@ -1,0 +1,82 @@
+"""GPU tests of the whole-proof glue: the library's verifier replays proofs written
+by the oracle prover and must return the oracle's (e, f, w, zw) bit for bit; the library's prover must write
+byte-identical proofs."""
+import numpy as np
+import pytest
+
+import circuits
+import halo2_aggregation_b200 as h2a
+from oracle import plonk as pk
+from oracle import pymodel as pm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = h2a.Context(0)
+    yield c
+    c.close()
+
+
+def pts_bytes(points):
+    return np.frombuffer(b"".join(pm.affine_bytes(p) for p in points), dtype=np.uint8)
+
+
+def frs_bytes(vals):
+    return np.frombuffer(b"".join(pm.fr_mont_bytes(v) for v in vals), dtype=np.uint8) if vals else np.zeros(0, np.uint8)
+
+
+def make_circuit(ctx, c, keys):
+    shape = c["shape"]
+    circ = h2a.Circuit(ctx, shape, frs_bytes(shape.constants))
+    circ.set_vk(pts_bytes(keys.fixed_commitments), pts_bytes(keys.sigma_commitments), frs_bytes([keys.vk_hash]))
+    return circ
+
+
+def efwzw_bytes(res):
+    return pts_bytes([res["e"], res["f"], res["w"], res["zw"]])
+
+
+@pytest.mark.parametrize("which", ["my_circuit", "wide"])
+def test_verifier_glue_matches_oracle(ctx, orc, which):
+    c = circuits.my_circuit(k=6, table_bits=4) if which == "my_circuit" else circuits.wide_circuit(k=6)
+    params, keys = circuits.setup(orc, c)
+    proof, inst = pk.create_proof(orc, params, c["shape"], keys, c["instance"], c["advice"], seed=11)
+    want = pk.verify_proof(c["shape"], keys.fixed_commitments, keys.sigma_commitments, keys.vk_hash, inst, proof)
+    assert pk.pairing_relation_holds(want, params.s)
+    circ = make_circuit(ctx, c, keys)
+    got = circ.verify(pts_bytes(inst), proof)
+    assert bytes(got) == bytes(efwzw_bytes(want))
+    # malformed proofs are refused with H2A_ERR_PROOF, never crash
+    for bad in (proof[:-1], proof + b"\0", proof[:40], b"\xff" * len(proof)):
+        with pytest.raises(h2a.H2AError) as e:
+            circ.verify(pts_bytes(inst), bad)
+        assert e.value.code == -5
+    # a flipped evaluation still parses but no longer satisfies the pairing relation
+    t = bytearray(proof)
+    t[32 * (c["shape"].num_advice + 2 * len(c["shape"].lookups) + 2 + len(c["shape"].lookups) + 1 + 4) + 1] ^= 1
+    got_bad = circ.verify(pts_bytes(inst), bytes(t))
+    want_bad = pk.verify_proof(c["shape"], keys.fixed_commitments, keys.sigma_commitments, keys.vk_hash, inst, bytes(t))
+    assert bytes(got_bad) == bytes(efwzw_bytes(want_bad)) and not pk.pairing_relation_holds(want_bad, params.s)
+    circ.free()
+
+
+def test_verifier_glue_batch_of_64(ctx, orc):
+    """BASELINE config 5: 64 proofs of the sample circuit, all 256 sums in one launch."""
+    c = circuits.my_circuit(k=5, table_bits=3)
+    params, keys = circuits.setup(orc, c)
+    circ = make_circuit(ctx, c, keys)
+    proofs, insts, wants = [], [], []
+    for s in range(8):
+        ci = circuits.my_circuit(k=5, table_bits=3, a=1 + s % 7, b=2 + s % 5, seed=s)   # same fixed columns, other witnesses
+        proof, inst = pk.create_proof(orc, params, ci["shape"], keys, ci["instance"], ci["advice"], seed=s)
+        proofs.append(proof); insts.append(inst[0])
+        wants.append(pk.verify_proof(ci["shape"], keys.fixed_commitments, keys.sigma_commitments, keys.vk_hash, inst, proof))
+    batch = [proofs[i % 8] for i in range(64)]
+    binst = pts_bytes([insts[i % 8] for i in range(64)])
+    got = circ.verify_batch(binst, batch)
+    for i in range(64):
+        assert bytes(got[i]) == bytes(efwzw_bytes(wants[i % 8])), i
+    assert all(pk.pairing_relation_holds(w, params.s) for w in wants)
+    circ.free()
