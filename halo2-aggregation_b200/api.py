@@ -59,6 +59,9 @@ def load_library():
     lib.h2a_phase_name.restype = ctypes.c_char_p
     lib.h2a_launch_count.restype = ctypes.c_uint64
     lib.h2a_bases_len.restype = c_sz
+    lib.h2a_blinds_len.restype = c_sz
+    lib.h2a_proof_len.restype = c_sz
+    lib.h2a_prove_phase_name.restype = ctypes.c_char_p
     lib.h2a_transcript_new.restype = ctypes.c_void_p
     lib.h2a_transcript_free.restype = None
     _LIB = lib
@@ -356,6 +359,41 @@ class Circuit:
     def set_vk(self, fixed_commitments, sigma_commitments, vk_hash):
         f, s = _bytes(fixed_commitments), _bytes(sigma_commitments)
         self.ctx._check(self.ctx.lib.h2a_circuit_set_vk(self.ctx.h, self.h, _ptr(f), _ptr(s), _ptr(_bytes(vk_hash))))
+
+    def set_keys(self, g, g_lagrange, fixed_values, sigmas, vk_hash, coset_shift):
+        """Proving key: Params bases handles + fixed / permutation columns (column-major, n elements each)."""
+        f, s = _bytes(fixed_values), _bytes(sigmas)
+        self.ctx._check(self.ctx.lib.h2a_circuit_set_keys(self.ctx.h, self.h, g.h, g_lagrange.h, _ptr(f) if f.size else None,
+                                                          _ptr(s) if s.size else None, _ptr(_bytes(vk_hash)), _ptr(_bytes(coset_shift))))
+        self._keep = (g, g_lagrange)
+
+    def get_vk(self, n_fixed, n_perm):
+        f, s = np.zeros(64 * n_fixed, np.uint8), np.zeros(64 * n_perm, np.uint8)
+        self.ctx._check(self.ctx.lib.h2a_circuit_get_vk(self.ctx.h, self.h, _ptr(f), _ptr(s)))
+        return f, s
+
+    def blinds_len(self):
+        return int(self.ctx.lib.h2a_blinds_len(self.h))
+
+    def proof_len(self):
+        return int(self.ctx.lib.h2a_proof_len(self.h))
+
+    def prove(self, instance_cols, advice_cols, blinds):
+        """create_proof: returns (proof bytes, instance commitments)."""
+        ic, ac, bl = _bytes(instance_cols), _bytes(advice_cols), _bytes(blinds)
+        if bl.size != 32 * self.blinds_len():
+            raise H2AError(-1, "prove: blinds has %d elements, expected %d" % (bl.size // 32, self.blinds_len()))
+        out = np.zeros(self.proof_len(), np.uint8)
+        ln = c_sz(0)
+        inst = np.zeros(64 * self.n_instance, np.uint8)
+        self.ctx._check(self.ctx.lib.h2a_create_proof(self.ctx.h, self.h, _ptr(ic) if ic.size else None, _ptr(ac) if ac.size else None,
+                                                      _ptr(bl), _ptr(out), c_sz(out.size), ctypes.byref(ln), _ptr(inst)))
+        return bytes(out[:ln.value]), inst
+
+    def prove_phases(self):
+        buf = (ctypes.c_float * 32)()
+        k = self.ctx.lib.h2a_prove_phase_ms(self.ctx.h, self.h, buf, 32)
+        return [((self.ctx.lib.h2a_prove_phase_name(self.ctx.h, i) or b"").decode(), float(buf[i])) for i in range(max(k, 0))]
 
     def verify(self, instance_commitments, proof):
         """(e, f, w, zw) of one proof: 256 bytes."""

@@ -33,6 +33,7 @@ struct h2a_ctx {
     std::vector<cudaEvent_t> ev;
     int ev_used = 0;
     std::vector<float> phase_ms;
+    std::vector<const char*> prove_phase_names;
 
     // MSM workspace
     DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc;

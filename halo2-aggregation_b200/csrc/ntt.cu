@@ -373,6 +373,23 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
     return H2A_OK;
 }
 
+// Public to the other translation units: out <- two-level power tables of `base` scaled by `c`
+// (lo at 0: c*base^i for i < 1024; hi at 32*1024: base^(1024*i)).
+int h2a_pow_tables(h2a_ctx* ctx, const uint8_t base[32], const uint8_t c[32], uint32_t n, DevBuf& out) {
+    return build_pow_tables(ctx, h2a_host::fr_load(base), h2a_host::fr_load(c), n, out);
+}
+// d_out[i] = c * base^i for i < n  (32-byte elements)
+int h2a_pow_vector(h2a_ctx* ctx, const uint8_t base[32], const uint8_t c[32], uint32_t n, uint8_t* d_out) {
+    DevBuf pw;
+    H2A_TRY(build_pow_tables(ctx, h2a_host::fr_load(base), h2a_host::fr_load(c), n, pw));
+    expand_pow_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>((uint8_t*)pw.p, (uint8_t*)pw.p + (32ull << LOG_PW_LO), n, d_out);
+    ctx->launches++;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(pw.p);
+    if (e != cudaSuccess) H2A_FAIL(ctx, H2A_ERR_CUDA, "pow_vector: %s", cudaGetErrorString(e));
+    return H2A_OK;
+}
+
 void h2a_ntt_free_tables(h2a_ctx* ctx) {
     for (auto& kv : ctx->ntt_tables) {
         NttTables* t = kv.second;

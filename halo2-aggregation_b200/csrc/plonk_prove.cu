@@ -1,4 +1,984 @@
-// plonk_prove.cu — prover pipeline (placeholder until the pipeline lands)
+// plonk_prove.cu — the prover pipeline that `create_proof` runs for the circuits the reference proves
+// (examples/simple-example.rs:606-613 sample proof, :702-709 aggregation proof), laid out on the device
+// around the MSM (msm.cu) and NTT (ntt.cu) kernels.  Step order = the order in which
+// `VerifierChip::_verify_proof` re-reads the proof (src/verifier.rs:341-510, :718-719, src/multiopen.rs:392):
+//
+//   instance/advice commitments -> theta -> lookup A', S' -> beta, gamma -> permutation Z -> lookup Z ->
+//   random polynomial -> y -> quotient h(X) on the extended coset, split, committed -> x -> evaluations ->
+//   v, u -> one KZG witness W_i per rotation set (ascending rotation).
+//
+// Everything data-parallel runs in kernels of this file (expression evaluation over rows, grand-product
+// prefix scans with batch inversion, quotient evaluation, Horner evaluation, v-combination, Kate division);
+// the host keeps the Blake2b transcript and, for now, the lookup permutation (a sort).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "field.cuh"
+#include "host_glue.hpp"
 #include "plonk.hpp"
-struct ProverState {};
-void h2a_prover_state_free(h2a_ctx*, ProverState* p) { delete p; }
+
+int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
+                const uint8_t omega[32], int inverse, const uint8_t* coset_shift);
+int h2a_pow_tables(h2a_ctx* ctx, const uint8_t base[32], const uint8_t c[32], uint32_t n, DevBuf& out);
+int h2a_pow_vector(h2a_ctx* ctx, const uint8_t base[32], const uint8_t c[32], uint32_t n, uint8_t* d_out);
+
+namespace hh = h2a_host;
+using h2a_plonk::Shape;
+
+constexpr int MAX_COLS = 64, MAX_Q = 96, MAX_LK = 16, MAX_PERM = 48, MAX_CHUNKS = 24, MAX_PROGS = 96;
+constexpr int LOG_PW = 10;
+
+// Column tables of one evaluation domain (the 2^k rows, or the 2^ext_k points of the extended coset).
+struct EvalTables {
+    const uint8_t* col[3][MAX_COLS];  // [advice | fixed | instance][column] -> m elements
+    uint32_t q_col[3][MAX_Q];
+    int32_t q_rot[3][MAX_Q];
+    const uint8_t* consts;
+    const uint32_t* code;  // all programs, (op, arg) pairs
+    uint32_t prog_off[MAX_PROGS], prog_len[MAX_PROGS];
+    uint32_t mask, step;   // m - 1, and the index distance of one rotation
+};
+
+struct QuotientArgs {
+    EvalTables t;
+    uint32_t n_gates;                                   // programs 0 .. n_gates-1
+    uint32_t n_lookups, lk_in_first[MAX_LK], lk_in_cnt[MAX_LK], lk_tab_first[MAX_LK], lk_tab_cnt[MAX_LK];
+    const uint8_t *lk_pa[MAX_LK], *lk_ps[MAX_LK], *lk_z[MAX_LK];
+    uint32_t n_perm, chunk_len, n_chunks, perm_type[MAX_PERM], perm_qidx[MAX_PERM];
+    const uint8_t* sigma[MAX_PERM];
+    const uint8_t* pz[MAX_CHUNKS];
+    alignas(16) uint8_t beta_delta[MAX_PERM][32];       // beta * delta^i
+    const uint8_t *l0, *llast, *lblind;
+    alignas(16) uint8_t beta[32];
+    alignas(16) uint8_t gamma[32];
+    alignas(16) uint8_t theta[32];
+    alignas(16) uint8_t y[32];
+    const uint8_t *x_lo, *x_hi;                         // X_i = g * omega_ext^i as two-level tables
+    const uint8_t* vanish_inv;                          // 1 / (X_i^n - 1), period vanish_mask + 1
+    uint32_t vanish_mask;
+    int32_t last_rot;
+    uint8_t* out;
+};
+
+namespace dev {
+using namespace h2a;
+
+__device__ __forceinline__ Fr ld(const uint8_t* p, uint32_t i) { return Fr::load(p + 32ull * i); }
+
+__device__ __forceinline__ Fr query(const EvalTables& t, int type, uint32_t q, uint32_t row) {
+    uint32_t idx = (row + (uint32_t)(t.q_rot[type][q] * (int32_t)t.step)) & t.mask;
+    return ld(t.col[type][t.q_col[type][q]], idx);
+}
+
+__device__ Fr eval_prog(const EvalTables& t, uint32_t prog, uint32_t row) {
+    Fr st[16];
+    int sp = 0;
+    const uint32_t* c = t.code + 2 * t.prog_off[prog];
+    for (uint32_t k = 0; k < t.prog_len[prog]; k++) {
+        const uint32_t op = c[2 * k], arg = c[2 * k + 1];
+        switch (op) {
+            case 0: st[sp++] = ld(t.consts, arg); break;
+            case 1: st[sp++] = query(t, 0, arg, row); break;
+            case 2: st[sp++] = query(t, 1, arg, row); break;
+            case 3: st[sp++] = query(t, 2, arg, row); break;
+            case 4: st[sp - 1] = st[sp - 1].neg(); break;
+            case 5: st[sp - 2] = st[sp - 2] + st[sp - 1]; sp--; break;
+            case 6: st[sp - 2] = st[sp - 2] * st[sp - 1]; sp--; break;
+            default: st[sp - 1] = st[sp - 1] * ld(t.consts, arg); break;
+        }
+    }
+    return st[0];
+}
+
+__device__ Fr compress(const EvalTables& t, uint32_t first, uint32_t cnt, const Fr& theta, uint32_t row) {
+    Fr acc = Fr::zero();
+    for (uint32_t p = 0; p < cnt; p++) acc = acc * theta + eval_prog(t, first + p, row);
+    return acc;
+}
+
+// out[row] = theta-compression of programs [first, first+cnt) at every row     (src/lookup.rs:229-262)
+__global__ void __launch_bounds__(128) compress_kernel(const EvalTables* t, uint32_t first, uint32_t cnt, const uint8_t* theta,
+                                                       uint32_t m, uint8_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    compress(*t, first, cnt, Fr::load(theta), i).store(out + 32ull * i);
+}
+
+// h(X_i) numerator folded with y, divided by the vanishing polynomial, for every point of the extended coset.
+// Expression order: gates, permutation 1-4 (src/permutation.rs:211-321), five per lookup (src/lookup.rs:190-310).
+__global__ void __launch_bounds__(128) quotient_kernel(const QuotientArgs* ap) {
+    const QuotientArgs& a = *ap;
+    const EvalTables& t = a.t;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > t.mask) return;
+    const Fr y = Fr::load(a.y), beta = Fr::load(a.beta), gamma = Fr::load(a.gamma), one = Fr::one();
+    Fr acc = Fr::zero();
+    for (uint32_t g = 0; g < a.n_gates; g++) acc = acc * y + eval_prog(t, g, i);
+    const Fr l0 = ld(a.l0, i), llast = ld(a.llast, i);
+    const Fr one_minus = one - (llast + ld(a.lblind, i));
+    const uint32_t nxt = (i + t.step) & t.mask, prv = (i - t.step) & t.mask;
+    if (a.n_chunks) {
+        acc = acc * y + l0 * (one - ld(a.pz[0], i));
+        Fr zl = ld(a.pz[a.n_chunks - 1], i);
+        acc = acc * y + llast * (zl.sqr() - zl);
+        const uint32_t lastidx = (i + (uint32_t)(a.last_rot * (int32_t)t.step)) & t.mask;
+        for (uint32_t c = 1; c < a.n_chunks; c++) acc = acc * y + l0 * (ld(a.pz[c], i) - ld(a.pz[c - 1], lastidx));
+        Fr x = ld(a.x_lo, i & ((1u << LOG_PW) - 1u));
+        if (i >> LOG_PW) x = x * ld(a.x_hi, i >> LOG_PW);
+        for (uint32_t c = 0; c < a.n_chunks; c++) {
+            Fr left = ld(a.pz[c], nxt), right = ld(a.pz[c], i);
+            const uint32_t hi = min((c + 1) * a.chunk_len, a.n_perm);
+            for (uint32_t k = c * a.chunk_len; k < hi; k++) {
+                Fr val = query(t, a.perm_type[k], a.perm_qidx[k], i);
+                left = left * (beta * ld(a.sigma[k], i) + val + gamma);
+                right = right * (Fr::load(a.beta_delta[k]) * x + val + gamma);
+            }
+            acc = acc * y + (left - right) * one_minus;
+        }
+    }
+    if (a.n_lookups) {
+        const Fr theta = Fr::load(a.theta);
+        for (uint32_t l = 0; l < a.n_lookups; l++) {
+            Fr z = ld(a.lk_z[l], i), zn = ld(a.lk_z[l], nxt), pa = ld(a.lk_pa[l], i), pap = ld(a.lk_pa[l], prv), ps = ld(a.lk_ps[l], i);
+            acc = acc * y + l0 * (one - z);
+            acc = acc * y + llast * (z.sqr() - z);
+            Fr ci = compress(t, a.lk_in_first[l], a.lk_in_cnt[l], theta, i);
+            Fr ct = compress(t, a.lk_tab_first[l], a.lk_tab_cnt[l], theta, i);
+            Fr left = (pa + beta) * (ps + gamma) * zn, right = (ci + beta) * (ct + gamma) * z;
+            acc = acc * y + (left - right) * one_minus;
+            acc = acc * y + l0 * (pa - ps);
+            acc = acc * y + (pa - ps) * (pa - pap) * one_minus;
+        }
+    }
+    (acc * ld(a.vanish_inv, i & a.vanish_mask)).store(a.out + 32ull * i);
+}
+
+struct PermTermArgs {
+    const uint8_t* vals[8];
+    const uint8_t* sigma[8];
+    alignas(16) uint8_t beta_delta[8][32];
+    uint32_t ncols;
+};
+// num[i] = prod_c (beta delta^c omega^i + gamma + v_c[i]);  den[i] = prod_c (beta sigma_c[i] + gamma + v_c[i])
+__global__ void __launch_bounds__(128) perm_terms_kernel(PermTermArgs a, const uint8_t* beta_, const uint8_t* gamma_,
+                                                         const uint8_t* omega_pows, uint32_t n, uint8_t* num, uint8_t* den) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr beta = Fr::load(beta_), gamma = Fr::load(gamma_), w = ld(omega_pows, i);
+    Fr nu = Fr::one(), de = Fr::one();
+    for (uint32_t c = 0; c < a.ncols; c++) {
+        Fr v = ld(a.vals[c], i);
+        nu = nu * (Fr::load(a.beta_delta[c]) * w + gamma + v);
+        de = de * (beta * ld(a.sigma[c], i) + gamma + v);
+    }
+    nu.store(num + 32ull * i);
+    de.store(den + 32ull * i);
+}
+// rows < usable: num = (A+beta)(S+gamma), den = (A'+beta)(S'+gamma); other rows 1      (src/lookup.rs:81-106)
+__global__ void __launch_bounds__(128) lookup_terms_kernel(const uint8_t* A, const uint8_t* S, const uint8_t* pa, const uint8_t* ps,
+                                                           const uint8_t* beta_, const uint8_t* gamma_, uint32_t usable, uint32_t n,
+                                                           uint8_t* num, uint8_t* den) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr nu = Fr::one(), de = Fr::one();
+    if (i < usable) {
+        const Fr beta = Fr::load(beta_), gamma = Fr::load(gamma_);
+        nu = (ld(A, i) + beta) * (ld(S, i) + gamma);
+        de = (ld(pa, i) + beta) * (ld(ps, i) + gamma);
+    }
+    nu.store(num + 32ull * i);
+    de.store(den + 32ull * i);
+}
+
+// In-place inversion, 16 elements per thread with one field inversion (Montgomery's trick); zeros stay zero.
+constexpr int INV_CHUNK = 16;
+__global__ void __launch_bounds__(128) batch_inverse_kernel(uint8_t* a, uint32_t n) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t lo = t * INV_CHUNK;
+    if (lo >= n) return;
+    uint32_t cnt = min((uint32_t)INV_CHUNK, n - lo);
+    Fr pre[INV_CHUNK];
+    Fr run = Fr::one();
+    for (uint32_t k = 0; k < cnt; k++) {
+        pre[k] = run;
+        Fr v = ld(a, lo + k);
+        if (!v.is_zero()) run = run * v;
+    }
+    Fr inv = run.inv();
+    for (int k = (int)cnt - 1; k >= 0; k--) {
+        Fr v = ld(a, lo + k);
+        if (v.is_zero()) continue;
+        (inv * pre[k]).store(a + 32ull * (lo + k));
+        inv = inv * v;
+    }
+}
+__global__ void mul_arrays_kernel(const uint8_t* a, const uint8_t* b, uint32_t n, uint8_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) (ld(a, i) * ld(b, i)).store(out + 32ull * i);
+}
+
+// ---- inclusive prefix product, in place: tiles of 2048 (256 threads x 8), recursion over the tile totals
+constexpr int SCAN_T = 256, SCAN_I = 8, SCAN_TILE = SCAN_T * SCAN_I;
+__global__ void __launch_bounds__(SCAN_T) scan_mul_tiles_kernel(uint8_t* data, uint32_t n, uint8_t* totals) {
+    __shared__ __align__(16) uint8_t sh[SCAN_T * 32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_I;
+    Fr v[SCAN_I];
+    Fr run = Fr::one();
+#pragma unroll
+    for (int k = 0; k < SCAN_I; k++) {
+        if (base + k < n) run = run * ld(data, base + k);
+        v[k] = run;
+    }
+    run.store(sh + 32 * threadIdx.x);
+    __syncthreads();
+    for (int d = 1; d < SCAN_T; d <<= 1) {  // Hillis-Steele over the thread totals
+        Fr mine = Fr::load(sh + 32 * threadIdx.x), other = Fr::one();
+        const bool has = (int)threadIdx.x >= d;
+        if (has) other = Fr::load(sh + 32 * (threadIdx.x - d));
+        __syncthreads();
+        if (has) (mine * other).store(sh + 32 * threadIdx.x);
+        __syncthreads();
+    }
+    Fr off = threadIdx.x ? Fr::load(sh + 32 * (threadIdx.x - 1)) : Fr::one();
+#pragma unroll
+    for (int k = 0; k < SCAN_I; k++)
+        if (base + k < n) (v[k] * off).store(data + 32ull * (base + k));
+    if (threadIdx.x == SCAN_T - 1) Fr::load(sh + 32 * (SCAN_T - 1)).store(totals + 32ull * blockIdx.x);
+}
+__global__ void scan_mul_apply_kernel(uint8_t* data, uint32_t n, const uint8_t* totals_inclusive) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t tile = i / SCAN_TILE;
+    if (i >= n || tile == 0) return;
+    (ld(data, i) * ld(totals_inclusive, tile - 1)).store(data + 32ull * i);
+}
+// z[0] = init, z[i] = init * incl[i-1]   (grand product column from the inclusive scan of the ratios)
+__global__ void shift_scale_kernel(const uint8_t* incl, const uint8_t* init_, uint32_t n, uint8_t* z) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr init = Fr::load(init_);
+    (i ? init * ld(incl, i - 1) : init).store(z + 32ull * i);
+}
+
+// ---- chunked Horner: thread t folds coefficients [t*L, (t+1)*L) at the point z
+constexpr int HORNER_L = 64;
+__device__ __forceinline__ Fr chunk_value(const uint8_t* coef, uint32_t n, uint32_t t, const Fr& z) {
+    Fr acc = Fr::zero();
+    const uint32_t lo = t * HORNER_L, hi = min(lo + HORNER_L, n);
+    for (uint32_t i = hi; i-- > lo;) acc = acc * z + ld(coef, i);
+    return acc;
+}
+__global__ void __launch_bounds__(128) chunk_values_kernel(const uint8_t* coef, uint32_t n, const uint8_t* z_, uint8_t* out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t * HORNER_L >= n) return;
+    chunk_value(coef, n, t, Fr::load(z_)).store(out + 32ull * t);
+}
+// p(z) = sum_t C_t (z^L)^t over the chunk values: one block, strided Horner then a shared-memory tree
+__global__ void __launch_bounds__(256) fold_chunks_kernel(const uint8_t* C, uint32_t nchunks, const uint8_t* z_, uint8_t* out) {
+    __shared__ __align__(16) uint8_t sh[256 * 32];
+    Fr z = Fr::load(z_), zl = z;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) zl = zl.sqr();  // z^64
+    // thread j takes chunks j, j+256, ...:  sum_m C_{j+256m} zl^(j+256m) = zl^j * Horner in zl^256
+    Fr zb = zl;
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) zb = zb.sqr();  // zl^256
+    Fr acc = Fr::zero();
+    uint32_t cnt = nchunks > threadIdx.x ? (nchunks - threadIdx.x + 255) / 256 : 0;
+    for (uint32_t m = cnt; m-- > 0;) acc = acc * zb + ld(C, threadIdx.x + 256 * m);
+    uint32_t e[1] = {threadIdx.x};
+    if (cnt) acc = acc * zl.pow_limbs(e, 8);
+    acc.store(sh + 32 * threadIdx.x);
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) (Fr::load(sh + 32 * threadIdx.x) + Fr::load(sh + 32 * (threadIdx.x + s))).store(sh + 32 * threadIdx.x);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) Fr::load(sh).store(out);
+}
+
+// acc[i] = acc[i] * v + p[i]                       (Horner in v over the polynomials of one rotation set)
+__global__ void axpy_kernel(uint8_t* acc, const uint8_t* p, const uint8_t* v_, uint32_t n, int first) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (first) ld(p, i).store(acc + 32ull * i);
+    else (ld(acc, i) * Fr::load(v_) + ld(p, i)).store(acc + 32ull * i);
+}
+
+// ---- Kate division q = (p - p(z)) / (X - z): q_j = sum_{i>j} p_i z^(i-j-1)
+// carries S_t = sum_{i >= (t+1)L} p_i z^(i-(t+1)L) from the chunk values: one block of 128 threads
+__global__ void __launch_bounds__(128) kate_carry_kernel(const uint8_t* C, uint32_t nchunks, const uint8_t* z_, uint8_t* S) {
+    __shared__ __align__(16) uint8_t shD[128 * 32];
+    __shared__ __align__(16) uint8_t shT[128 * 32];
+    Fr z = Fr::load(z_), zl = z;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) zl = zl.sqr();                    // z^L
+    const uint32_t M = (nchunks + 127) / 128;                     // chunks per thread
+    const uint32_t lo = threadIdx.x * M, hi = min(lo + M, nchunks);
+    Fr D = Fr::zero();                                            // D_s = sum_{j<M} C_{lo+j} zl^j
+    for (uint32_t t = hi; t-- > lo && t < nchunks;) D = D * zl + ld(C, t);
+    D.store(shD + 32 * threadIdx.x);
+    __syncthreads();
+    if (threadIdx.x == 0) {                                       // T_s = carry into the top chunk of group s
+        uint32_t e[1] = {M};
+        Fr zlm = zl.pow_limbs(e, 32 - __clz(M | 1));
+        Fr T = Fr::zero();
+        for (int s = 127; s >= 0; s--) {
+            T.store(shT + 32 * s);
+            T = Fr::load(shD + 32 * s) + zlm * T;
+        }
+    }
+    __syncthreads();
+    if (lo < nchunks) {
+        Fr carry = Fr::load(shT + 32 * threadIdx.x);
+        for (uint32_t t = hi; t-- > lo;) {
+            carry.store(S + 32ull * t);
+            carry = ld(C, t) + zl * carry;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) kate_quotient_kernel(const uint8_t* p, uint32_t n, const uint8_t* z_, const uint8_t* S, uint8_t* q) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lo = t * HORNER_L;
+    if (lo >= n) return;
+    const uint32_t hi = min(lo + HORNER_L, n);
+    Fr z = Fr::load(z_), carry = ld(S, t);
+    for (uint32_t i = hi; i-- > lo;) {
+        Fr pi = ld(p, i);
+        carry.store(q + 32ull * i);
+        carry = pi + z * carry;
+    }
+}
+
+}  // namespace dev
+
+// ====================================================================== host side
+struct Poly3 {
+    uint8_t *lag = nullptr, *coef = nullptr, *ext = nullptr;
+};
+
+struct ProverState {
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0, used = 0;
+    const h2a_bases *g = nullptr, *g_lagrange = nullptr;
+    uint8_t coset[32];
+    std::vector<Poly3> fixed, sigma, advice, instance, pz;
+    struct Lk { uint8_t *A, *S; Poly3 pa, ps, z; };
+    std::vector<Lk> lk;
+    uint8_t *l0 = nullptr, *llast = nullptr, *lblind = nullptr;          // extended
+    uint8_t *random_coef = nullptr, *h_ext = nullptr, *h_coef = nullptr;
+    uint8_t *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr}, *tmp_m = nullptr;
+    uint8_t *omega_pows = nullptr;                                        // omega^i, i < n
+    uint8_t *chunks = nullptr, *carries = nullptr, *totals = nullptr, *small = nullptr;
+    DevBuf xtab;                                                          // g * omega_ext^i two-level
+    uint8_t *vanish_inv = nullptr;
+    uint32_t* code = nullptr;
+    uint8_t* consts = nullptr;
+    EvalTables* d_tab_n = nullptr;
+    QuotientArgs* d_qargs = nullptr;
+    EvalTables tab_n;
+    QuotientArgs qargs;
+    std::vector<float> phase_ms;
+};
+
+void h2a_prover_state_free(h2a_ctx* ctx, ProverState* p) {
+    if (!p) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (p->arena) cudaFree(p->arena);
+    if (p->xtab.p) cudaFree(p->xtab.p);
+    delete p;
+}
+
+namespace {
+
+uint8_t* arena_take(ProverState* p, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    uint8_t* r = p->arena + p->used;
+    p->used += bytes;
+    return r;
+}
+
+struct Stepper {  // phase timing with events on the ctx stream
+    h2a_ctx* ctx;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> names;
+    void mark(const char* name) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, ctx->stream);
+        ev.push_back(e);
+        names.push_back(name);
+    }
+};
+
+#define LAUNCH1D(kernel, count, threads, ...)                                                  \
+    do {                                                                                       \
+        kernel<<<(unsigned)(((count) + (threads)-1) / (threads)), (threads), 0, ctx->stream>>>(__VA_ARGS__); \
+        H2A_LAUNCH_CHECK(ctx);                                                                 \
+    } while (0)
+
+int upload_fr(h2a_ctx* ctx, uint8_t* d, const hh::Fr& v) {
+    uint8_t b[32];
+    hh::fr_store(b, v);
+    H2A_CUDA(ctx, cudaMemcpyAsync(d, b, 32, cudaMemcpyHostToDevice, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // b is a stack buffer
+    return H2A_OK;
+}
+
+int to_coef(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* lag, uint8_t* coef) {
+    uint8_t w[32];
+    hh::fr_store(w, c->shape.omega);
+    return h2a_ntt_run(ctx, lag, c->shape.n, c->prover->tmp_n[3], coef, c->shape.k, w, 1, nullptr);
+}
+int to_ext(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* coef, uint8_t* ext) {
+    uint8_t w[32];
+    hh::fr_store(w, hh::fr_root_of_unity((int)c->shape.ext_k));
+    return h2a_ntt_run(ctx, coef, c->shape.n, c->prover->tmp_m, ext, c->shape.ext_k, w, 0, c->prover->coset);
+}
+int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint32_t n, hh::PointA& out) {
+    uint8_t b[64];
+    H2A_TRY(h2a_msm_run(ctx, bases, 0, d_scalars, n, b));
+    out = hh::affine_load(b);
+    return H2A_OK;
+}
+
+// inclusive prefix product of a[0..n) in place (tiles, then recursion over the tile totals)
+int scan_mul(h2a_ctx* ctx, uint8_t* a, uint32_t n, uint8_t* totals) {
+    const uint32_t tiles = (n + dev::SCAN_TILE - 1) / dev::SCAN_TILE;
+    dev::scan_mul_tiles_kernel<<<tiles, dev::SCAN_T, 0, ctx->stream>>>(a, n, totals);
+    H2A_LAUNCH_CHECK(ctx);
+    if (tiles > 1) {
+        H2A_TRY(scan_mul(ctx, totals, tiles, totals + 32ull * ((tiles + 7) & ~7u)));
+        LAUNCH1D(dev::scan_mul_apply_kernel, n, 256, a, n, totals);
+    }
+    return H2A_OK;
+}
+
+// value of the polynomial at z (z already on the device at d_z); result lands in d_out (device)
+int eval_poly(h2a_ctx* ctx, ProverState* p, const uint8_t* coef, uint32_t n, const uint8_t* d_z, uint8_t* d_out) {
+    const uint32_t nchunks = (n + dev::HORNER_L - 1) / dev::HORNER_L;
+    LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, coef, n, d_z, p->chunks);
+    dev::fold_chunks_kernel<<<1, 256, 0, ctx->stream>>>(p->chunks, nchunks, d_z, d_out);
+    H2A_LAUNCH_CHECK(ctx);
+    return H2A_OK;
+}
+
+struct Raw256 {
+    uint64_t v[4];
+    bool operator<(const Raw256& o) const {
+        for (int i = 3; i >= 0; i--)
+            if (v[i] != o.v[i]) return v[i] < o.v[i];
+        return false;
+    }
+    bool operator==(const Raw256& o) const { return memcmp(v, o.v, 32) == 0; }
+};
+
+// halo2 `permute_expression_pair` on the usable rows: A' = sorted inputs; S' puts each distinct input's table
+// entry on the row of its first occurrence and the left-over table entries (ascending) on the repeated rows,
+// filled from the last repeated row backwards.  Host side for now.
+bool permute_lookup(const std::vector<uint8_t>& A, const std::vector<uint8_t>& S, uint32_t u, std::vector<uint8_t>& pa,
+                    std::vector<uint8_t>& ps) {
+    std::vector<Raw256> a(u), s(u);
+    for (uint32_t i = 0; i < u; i++) {
+        hh::fr_to_raw(hh::fr_load(A.data() + 32 * i), a[i].v);
+        hh::fr_to_raw(hh::fr_load(S.data() + 32 * i), s[i].v);
+    }
+    std::sort(a.begin(), a.end());
+    std::sort(s.begin(), s.end());
+    std::vector<char> used(u, 0), filled(u, 0);
+    std::vector<Raw256> out(u);
+    std::vector<uint32_t> repeated;
+    uint32_t j = 0;
+    for (uint32_t row = 0; row < u; row++) {
+        if (row == 0 || !(a[row] == a[row - 1])) {
+            while (j < u && s[j] < a[row]) j++;
+            if (j >= u || !(s[j] == a[row])) return false;  // input value absent from the table
+            used[j++] = 1;
+            out[row] = a[row];
+            filled[row] = 1;
+        } else {
+            repeated.push_back(row);
+        }
+    }
+    size_t r = repeated.size();
+    for (uint32_t t = 0; t < u; t++)
+        if (!used[t]) out[repeated[--r]] = s[t];
+    pa.resize(32 * (size_t)u);
+    ps.resize(32 * (size_t)u);
+    for (uint32_t i = 0; i < u; i++) {
+        hh::fr_store(pa.data() + 32 * i, hh::fr_from_raw(a[i].v));
+        hh::fr_store(ps.data() + 32 * i, hh::fr_from_raw(out[i].v));
+    }
+    return true;
+}
+
+void compress_point(const hh::PointA& p, uint8_t out[32]) {
+    if (hh::is_identity(p)) { memset(out, 0, 32); return; }
+    uint64_t x[4], y[4];
+    hh::fq_to_raw(p.x, x);
+    hh::fq_to_raw(p.y, y);
+    memcpy(out, x, 32);
+    out[31] |= (uint8_t)((y[0] & 1) << 7);
+}
+
+hh::Fr rotate_point(const Shape& s, const hh::Fr& x, int32_t rot) {
+    return x * (rot >= 0 ? hh::pow_u64(s.omega, (uint64_t)rot) : hh::pow_u64(s.omega_inv, (uint64_t)(-(int64_t)rot)));
+}
+
+}  // namespace
+
+extern "C" {
+
+// Loads the proving key: commits the fixed columns and the permutation polynomials (so the vk is set too) and
+// keeps their coefficient and extended-coset forms resident.
+int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const h2a_bases* g_lagrange, const uint8_t* fixed_values,
+                         const uint8_t* sigmas, const uint8_t vk_hash[32], const uint8_t coset_shift[32]) {
+    if (!ctx || !c || !g || !g_lagrange || !vk_hash || !coset_shift) return H2A_ERR_INVALID;
+    const Shape& s = c->shape;
+    const uint32_t n = s.n, m = 1u << s.ext_k;
+    if (g->n < n || g_lagrange->n < n) H2A_FAIL(ctx, H2A_ERR_INVALID, "set_keys: params hold fewer than %u bases", n);
+    if (s.n_advice > MAX_COLS || s.n_fixed > MAX_COLS || s.n_instance > MAX_COLS || s.aq.size() > MAX_Q || s.fq.size() > MAX_Q ||
+        s.iq.size() > MAX_Q || s.lookups.size() > MAX_LK || s.perm.size() > MAX_PERM || s.n_chunks > MAX_CHUNKS || s.chunk_len > 8)
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "set_keys: circuit exceeds the prover's column/query limits");
+    if (c->prover) h2a_prover_state_free(ctx, c->prover);
+    ProverState* p = c->prover = new ProverState();
+    p->g = g;
+    p->g_lagrange = g_lagrange;
+    memcpy(p->coset, coset_shift, 32);
+
+    // programs: gates first, then per lookup its inputs then its tables
+    std::vector<uint32_t> code;
+    std::vector<uint32_t> off, len;
+    auto push = [&](const h2a_plonk::Prog& g_) { off.push_back((uint32_t)code.size() / 2); len.push_back((uint32_t)g_.code.size() / 2); code.insert(code.end(), g_.code.begin(), g_.code.end()); };
+    for (auto& g_ : s.gates) push(g_);
+    std::vector<uint32_t> in_first, tab_first;
+    for (auto& l : s.lookups) {
+        in_first.push_back((uint32_t)off.size());
+        for (auto& g_ : l.inputs) push(g_);
+        tab_first.push_back((uint32_t)off.size());
+        for (auto& g_ : l.tables) push(g_);
+    }
+    if (off.size() > MAX_PROGS) H2A_FAIL(ctx, H2A_ERR_INVALID, "set_keys: more than %d expression programs", MAX_PROGS);
+
+    // arena
+    const size_t nl = s.lookups.size();
+    const size_t n_arrays = 2 * (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * (2 + 6) + 1 + 4 + 1 + 8;
+    const size_t m_arrays = (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * 3 + 3 + 2 + 1;
+    p->arena_bytes = n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
+                     sizeof(EvalTables) + sizeof(QuotientArgs);
+    H2A_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
+    auto poly3 = [&]() { Poly3 q; q.lag = arena_take(p, 32ull * n); q.coef = arena_take(p, 32ull * n); q.ext = arena_take(p, 32ull * m); return q; };
+    for (uint32_t i = 0; i < s.n_fixed; i++) p->fixed.push_back(poly3());
+    for (size_t i = 0; i < s.perm.size(); i++) p->sigma.push_back(poly3());
+    for (uint32_t i = 0; i < s.n_advice; i++) p->advice.push_back(poly3());
+    for (uint32_t i = 0; i < s.n_instance; i++) p->instance.push_back(poly3());
+    for (uint32_t i = 0; i < s.n_chunks; i++) p->pz.push_back(poly3());
+    for (size_t i = 0; i < nl; i++) {
+        ProverState::Lk l;
+        l.A = arena_take(p, 32ull * n);
+        l.S = arena_take(p, 32ull * n);
+        l.pa = poly3(); l.ps = poly3(); l.z = poly3();
+        p->lk.push_back(l);
+    }
+    p->l0 = arena_take(p, 32ull * m); p->llast = arena_take(p, 32ull * m); p->lblind = arena_take(p, 32ull * m);
+    p->random_coef = arena_take(p, 32ull * n);
+    p->h_ext = arena_take(p, 32ull * m);
+    p->h_coef = arena_take(p, 32ull * m);
+    for (int i = 0; i < 4; i++) p->tmp_n[i] = arena_take(p, 32ull * n);
+    p->tmp_m = arena_take(p, 32ull * m);
+    p->omega_pows = arena_take(p, 32ull * n);
+    p->chunks = arena_take(p, 32ull * (m / dev::HORNER_L + 64));
+    p->carries = arena_take(p, 32ull * (m / dev::HORNER_L + 64));
+    p->totals = arena_take(p, 32ull * (n / dev::SCAN_TILE + 4096));
+    p->small = arena_take(p, 32 * 1024);
+    p->vanish_inv = arena_take(p, 32ull * (m / n));
+    p->code = (uint32_t*)arena_take(p, code.size() * 4 + 16);
+    p->consts = arena_take(p, 32 * s.consts.size() + 32);
+    p->d_tab_n = (EvalTables*)arena_take(p, sizeof(EvalTables));
+    p->d_qargs = (QuotientArgs*)arena_take(p, sizeof(QuotientArgs));
+    if (p->used > p->arena_bytes) H2A_FAIL(ctx, H2A_ERR_OOM, "set_keys: arena estimate too small (%zu > %zu)", p->used, p->arena_bytes);
+
+    if (!code.empty()) H2A_CUDA(ctx, cudaMemcpyAsync(p->code, code.data(), code.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint8_t> cb(32 * s.consts.size() + 32, 0);
+    for (size_t i = 0; i < s.consts.size(); i++) hh::fr_store(cb.data() + 32 * i, s.consts[i]);
+    H2A_CUDA(ctx, cudaMemcpyAsync(p->consts, cb.data(), cb.size(), cudaMemcpyHostToDevice, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    // omega^i and X_i = g * omega_ext^i
+    uint8_t wb[32], oneb[32];
+    hh::fr_store(oneb, hh::fr_one());
+    hh::fr_store(wb, s.omega);
+    H2A_TRY(h2a_pow_vector(ctx, wb, oneb, n, p->omega_pows));
+    hh::Fr w_ext = hh::fr_root_of_unity((int)s.ext_k), gshift = hh::fr_load(coset_shift);
+    hh::fr_store(wb, w_ext);
+    H2A_TRY(h2a_pow_tables(ctx, wb, coset_shift, m, p->xtab));
+    {   // 1 / (X_i^n - 1) has period m / n
+        std::vector<uint8_t> vb(32ull * (m / n));
+        hh::Fr gn = gshift, wn = w_ext;
+        for (uint32_t i = 0; i < s.k; i++) { gn = hh::sqr(gn); wn = hh::sqr(wn); }
+        hh::Fr cur = gn;
+        for (uint32_t j = 0; j < m / n; j++) { hh::fr_store(vb.data() + 32 * j, hh::inv(cur - hh::fr_one())); cur = cur * wn; }
+        H2A_CUDA(ctx, cudaMemcpyAsync(p->vanish_inv, vb.data(), vb.size(), cudaMemcpyHostToDevice, ctx->stream));
+        H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    // fixed + sigma: values, commitments, coefficient and extended forms
+    c->fixed_comms.assign(64 * (size_t)s.n_fixed, 0);
+    c->sigma_comms.assign(64 * s.perm.size(), 0);
+    for (uint32_t i = 0; i < s.n_fixed + s.perm.size(); i++) {
+        const bool is_fixed = i < s.n_fixed;
+        Poly3& q = is_fixed ? p->fixed[i] : p->sigma[i - s.n_fixed];
+        const uint8_t* src = is_fixed ? fixed_values + 32ull * n * i : sigmas + 32ull * n * (i - s.n_fixed);
+        H2A_CUDA(ctx, cudaMemcpyAsync(q.lag, src, 32ull * n, cudaMemcpyHostToDevice, ctx->stream));
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, g_lagrange, q.lag, n, cm));
+        hh::affine_store((is_fixed ? c->fixed_comms.data() + 64 * i : c->sigma_comms.data() + 64 * (i - s.n_fixed)), cm);
+        H2A_TRY(to_coef(ctx, c, q.lag, q.coef));
+        H2A_TRY(to_ext(ctx, c, q.coef, q.ext));
+    }
+    {   // l_0, l_last, l_blind on the extended coset
+        std::vector<uint8_t> lag(32ull * n, 0);
+        uint8_t* dst[3] = {p->l0, p->llast, p->lblind};
+        for (int which = 0; which < 3; which++) {
+            std::fill(lag.begin(), lag.end(), 0);
+            if (which == 0) hh::fr_store(lag.data(), hh::fr_one());
+            if (which == 1) hh::fr_store(lag.data() + 32ull * s.usable, hh::fr_one());
+            if (which == 2) for (uint32_t r = s.usable + 1; r < n; r++) hh::fr_store(lag.data() + 32ull * r, hh::fr_one());
+            H2A_CUDA(ctx, cudaMemcpyAsync(p->tmp_n[0], lag.data(), lag.size(), cudaMemcpyHostToDevice, ctx->stream));
+            H2A_TRY(to_coef(ctx, c, p->tmp_n[0], p->tmp_n[1]));
+            H2A_TRY(to_ext(ctx, c, p->tmp_n[1], dst[which]));
+            H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    memcpy(c->vk_hash, vk_hash, 32);
+    c->has_vk = true;
+
+    // evaluation tables
+    auto fill_tables = [&](EvalTables& t, bool ext) {
+        memset(&t, 0, sizeof t);
+        for (uint32_t i = 0; i < s.n_advice; i++) t.col[0][i] = ext ? p->advice[i].ext : p->advice[i].lag;
+        for (uint32_t i = 0; i < s.n_fixed; i++) t.col[1][i] = ext ? p->fixed[i].ext : p->fixed[i].lag;
+        for (uint32_t i = 0; i < s.n_instance; i++) t.col[2][i] = ext ? p->instance[i].ext : p->instance[i].lag;
+        const std::vector<h2a_plonk::Query>* qs[3] = {&s.aq, &s.fq, &s.iq};
+        for (int ty = 0; ty < 3; ty++)
+            for (size_t i = 0; i < qs[ty]->size(); i++) { t.q_col[ty][i] = (*qs[ty])[i].col; t.q_rot[ty][i] = (*qs[ty])[i].rot; }
+        t.consts = p->consts;
+        t.code = p->code;
+        for (size_t i = 0; i < off.size(); i++) { t.prog_off[i] = off[i]; t.prog_len[i] = len[i]; }
+        t.mask = (ext ? m : n) - 1;
+        t.step = ext ? m / n : 1;
+    };
+    fill_tables(p->tab_n, false);
+    QuotientArgs& qa = p->qargs;
+    memset(&qa, 0, sizeof qa);
+    fill_tables(qa.t, true);
+    qa.n_gates = (uint32_t)s.gates.size();
+    qa.n_lookups = (uint32_t)nl;
+    for (size_t i = 0; i < nl; i++) {
+        qa.lk_in_first[i] = in_first[i]; qa.lk_in_cnt[i] = (uint32_t)s.lookups[i].inputs.size();
+        qa.lk_tab_first[i] = tab_first[i]; qa.lk_tab_cnt[i] = (uint32_t)s.lookups[i].tables.size();
+        qa.lk_pa[i] = p->lk[i].pa.ext; qa.lk_ps[i] = p->lk[i].ps.ext; qa.lk_z[i] = p->lk[i].z.ext;
+    }
+    qa.n_perm = (uint32_t)s.perm.size(); qa.chunk_len = s.chunk_len; qa.n_chunks = s.n_chunks;
+    for (size_t i = 0; i < s.perm.size(); i++) { qa.perm_type[i] = s.perm[i].type; qa.perm_qidx[i] = s.perm[i].qidx; qa.sigma[i] = p->sigma[i].ext; }
+    for (uint32_t i = 0; i < s.n_chunks; i++) qa.pz[i] = p->pz[i].ext;
+    qa.l0 = p->l0; qa.llast = p->llast; qa.lblind = p->lblind;
+    qa.x_lo = (const uint8_t*)p->xtab.p; qa.x_hi = qa.x_lo + (32ull << LOG_PW);
+    qa.vanish_inv = p->vanish_inv; qa.vanish_mask = m / n - 1;
+    qa.last_rot = s.last_rot;
+    qa.out = p->h_ext;
+    H2A_CUDA(ctx, cudaMemcpyAsync(p->d_tab_n, &p->tab_n, sizeof(EvalTables), cudaMemcpyHostToDevice, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
+
+int h2a_circuit_get_vk(h2a_ctx* ctx, const h2a_circuit* c, uint8_t* fixed_comms, uint8_t* sigma_comms) {
+    if (!ctx || !c) return H2A_ERR_INVALID;
+    if (!c->has_vk) H2A_FAIL(ctx, H2A_ERR_INVALID, "get_vk: no key set");
+    if (fixed_comms && !c->fixed_comms.empty()) memcpy(fixed_comms, c->fixed_comms.data(), c->fixed_comms.size());
+    if (sigma_comms && !c->sigma_comms.empty()) memcpy(sigma_comms, c->sigma_comms.data(), c->sigma_comms.size());
+    return H2A_OK;
+}
+
+size_t h2a_blinds_len(const h2a_circuit* c) {
+    if (!c) return 0;
+    const Shape& s = c->shape;
+    return s.lookups.size() * (2 * (size_t)(s.bf + 1) + s.bf) + (size_t)s.n_chunks * s.bf + s.n;
+}
+
+size_t h2a_proof_len(const h2a_circuit* c) {
+    if (!c) return 0;
+    const Shape& s = c->shape;
+    std::map<int32_t, int> rots;
+    for (auto& q : s.iq) rots[q.rot] = 1;
+    for (auto& q : s.aq) rots[q.rot] = 1;
+    for (auto& q : s.fq) rots[q.rot] = 1;
+    rots[0] = 1;
+    if (s.n_chunks) rots[1] = 1;
+    if (s.n_chunks > 1) rots[s.last_rot] = 1;
+    if (!s.lookups.empty()) { rots[1] = 1; rots[-1] = 1; }
+    size_t points = s.n_advice + 3 * s.lookups.size() + s.n_chunks + 1 + s.qdeg + rots.size();
+    size_t scalars = s.iq.size() + s.aq.size() + s.fq.size() + 1 + s.perm.size() + (s.n_chunks ? 3 * (size_t)s.n_chunks - 1 : 0) +
+                     5 * s.lookups.size();
+    return 32 * (points + scalars);
+}
+
+int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols, const uint8_t* advice_cols, const uint8_t* blinds,
+                     uint8_t* proof_out, size_t proof_cap, size_t* proof_len, uint8_t* inst_comms_out) {
+    if (!ctx || !c || !proof_out || !proof_len || !blinds) return H2A_ERR_INVALID;
+    ProverState* p = c->prover;
+    if (!p) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: no proving key (h2a_circuit_set_keys)");
+    const Shape& s = c->shape;
+    const uint32_t n = s.n, m = 1u << s.ext_k, u = s.usable, bf = s.bf;
+    if (proof_cap < h2a_proof_len(c)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: output buffer too small");
+    if ((s.n_instance && !instance_cols) || (s.n_advice && !advice_cols)) return H2A_ERR_INVALID;
+    cudaStream_t st = ctx->stream;
+    Stepper steps{ctx};
+    steps.mark("start");
+
+    h2a_glue::Transcript tr;
+    size_t pos = 0;
+    auto write_point = [&](const hh::PointA& pt) { tr.common_point(pt); compress_point(pt, proof_out + pos); pos += 32; };
+    auto write_scalar = [&](const hh::Fr& v) { tr.common_scalar(v); uint64_t raw[4]; hh::fr_to_raw(v, raw); memcpy(proof_out + pos, raw, 32); pos += 32; };
+    const uint8_t* bl = blinds;
+
+    // small device scalars: slots of 32 bytes in p->small
+    auto slot = [&](int i) { return p->small + 32 * i; };
+    enum { S_THETA = 0, S_BETA, S_GAMMA, S_Y, S_V, S_INIT, S_Z0, S_EVAL0 = 16 };
+
+    tr.common_scalar(hh::fr_load(c->vk_hash));                                     // src/verifier.rs:341-358
+    for (uint32_t i = 0; i < s.n_instance; i++) {                                  // :360-363
+        H2A_CUDA(ctx, cudaMemcpyAsync(p->instance[i].lag, instance_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g_lagrange, p->instance[i].lag, n, cm));
+        if (!tr.common_point(cm)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
+        if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cm);
+    }
+    for (uint32_t i = 0; i < s.n_advice; i++) {                                    // :365-376
+        H2A_CUDA(ctx, cudaMemcpyAsync(p->advice[i].lag, advice_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g_lagrange, p->advice[i].lag, n, cm));
+        write_point(cm);
+    }
+    steps.mark("instance+advice commitments");
+    hh::Fr theta = tr.squeeze();                                                   // :378
+    H2A_TRY(upload_fr(ctx, slot(S_THETA), theta));
+
+    for (size_t li = 0; li < s.lookups.size(); li++) {                             // :380-387, src/lookup.rs:49-79
+        ProverState::Lk& l = p->lk[li];
+        LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_in_first[li], p->qargs.lk_in_cnt[li], slot(S_THETA), n, l.A);
+        LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_tab_first[li], p->qargs.lk_tab_cnt[li], slot(S_THETA), n, l.S);
+        std::vector<uint8_t> A(32ull * u), S(32ull * u), pa, ps;
+        H2A_CUDA(ctx, cudaMemcpyAsync(A.data(), l.A, A.size(), cudaMemcpyDeviceToHost, st));
+        H2A_CUDA(ctx, cudaMemcpyAsync(S.data(), l.S, S.size(), cudaMemcpyDeviceToHost, st));
+        H2A_CUDA(ctx, cudaStreamSynchronize(st));
+        if (!permute_lookup(A, S, u, pa, ps)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: lookup %zu has an input value absent from its table", li);
+        H2A_CUDA(ctx, cudaMemcpyAsync(l.pa.lag, pa.data(), pa.size(), cudaMemcpyHostToDevice, st));
+        H2A_CUDA(ctx, cudaMemcpyAsync(l.ps.lag, ps.data(), ps.size(), cudaMemcpyHostToDevice, st));
+        H2A_CUDA(ctx, cudaMemcpyAsync(l.pa.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
+        bl += 32ull * (n - u);
+        H2A_CUDA(ctx, cudaMemcpyAsync(l.ps.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
+        bl += 32ull * (n - u);
+        bl += 32ull * bf;  // this lookup's Z tail, consumed after beta and gamma
+        hh::PointA ca, cs;
+        H2A_TRY(commit(ctx, p->g_lagrange, l.pa.lag, n, ca));
+        H2A_TRY(commit(ctx, p->g_lagrange, l.ps.lag, n, cs));
+        write_point(ca);
+        write_point(cs);
+    }
+    steps.mark("lookup permuted columns");
+    hh::Fr beta = tr.squeeze(), gamma = tr.squeeze();                              // :390,393
+    H2A_TRY(upload_fr(ctx, slot(S_BETA), beta));
+    H2A_TRY(upload_fr(ctx, slot(S_GAMMA), gamma));
+
+    static const uint64_t DELTA_RAW[4] = {0x870e56bbe533e9a2ull, 0x5b5f898e5e963f25ull, 0x64ec26aad4c86e71ull, 0x09226b6e22c6f0caull};
+    const hh::Fr delta = hh::fr_from_raw(DELTA_RAW);
+    {   // beta * delta^i for the quotient kernel
+        hh::Fr bd = beta;
+        for (size_t i = 0; i < s.perm.size(); i++) { hh::fr_store(p->qargs.beta_delta[i], bd); bd = bd * delta; }
+    }
+    auto column_lag = [&](const h2a_plonk::PermCol& pc) {
+        return pc.type == h2a_plonk::COL_ADVICE ? p->advice[pc.col].lag : pc.type == h2a_plonk::COL_FIXED ? p->fixed[pc.col].lag : p->instance[pc.col].lag;
+    };
+    // blinds of the lookup grand products come before the permutation ones in the buffer: remember the cursor
+    const uint8_t* bl_lookup_z[MAX_LK];
+    // layout: per lookup (A' tail, S' tail, Z tail) — Z tails were skipped above; recompute cursors explicitly
+    {
+        const uint8_t* b = blinds;
+        for (size_t li = 0; li < s.lookups.size(); li++) { b += 64ull * (n - u); bl_lookup_z[li] = b; b += 32ull * bf; }
+        bl = b;  // permutation blinds start here
+    }
+    H2A_TRY(upload_fr(ctx, slot(S_INIT), hh::fr_one()));
+    for (uint32_t ci = 0; ci < s.n_chunks; ci++) {                                 // :402-409, src/permutation.rs:48-78
+        dev::PermTermArgs a;
+        memset(&a, 0, sizeof a);
+        const uint32_t lo = ci * s.chunk_len, hi = (uint32_t)std::min<size_t>((ci + 1) * s.chunk_len, s.perm.size());
+        a.ncols = hi - lo;
+        for (uint32_t k = lo; k < hi; k++) {
+            a.vals[k - lo] = column_lag(s.perm[k]);
+            a.sigma[k - lo] = p->sigma[k].lag;
+            memcpy(a.beta_delta[k - lo], p->qargs.beta_delta[k], 32);
+        }
+        LAUNCH1D(dev::perm_terms_kernel, n, 128, a, slot(S_BETA), slot(S_GAMMA), p->omega_pows, n, p->tmp_n[0], p->tmp_n[1]);
+        LAUNCH1D(dev::batch_inverse_kernel, (n + dev::INV_CHUNK - 1) / dev::INV_CHUNK, 128, p->tmp_n[1], n);
+        LAUNCH1D(dev::mul_arrays_kernel, n, 256, p->tmp_n[0], p->tmp_n[1], n, p->tmp_n[2]);
+        H2A_TRY(scan_mul(ctx, p->tmp_n[2], n, p->totals));
+        LAUNCH1D(dev::shift_scale_kernel, n, 256, p->tmp_n[2], slot(S_INIT), n, p->pz[ci].lag);
+        // last_z of this chunk (row `usable`) seeds the next chunk, read before the blinds overwrite the tail
+        H2A_CUDA(ctx, cudaMemcpyAsync(slot(S_INIT), p->pz[ci].lag + 32ull * u, 32, cudaMemcpyDeviceToDevice, st));
+        H2A_CUDA(ctx, cudaMemcpyAsync(p->pz[ci].lag + 32ull * (n - bf), bl, 32ull * bf, cudaMemcpyHostToDevice, st));
+        bl += 32ull * bf;
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g_lagrange, p->pz[ci].lag, n, cm));
+        write_point(cm);
+    }
+    steps.mark("permutation grand products");
+    for (size_t li = 0; li < s.lookups.size(); li++) {                             // :411-417, src/lookup.rs:81-106
+        ProverState::Lk& l = p->lk[li];
+        LAUNCH1D(dev::lookup_terms_kernel, n, 128, l.A, l.S, l.pa.lag, l.ps.lag, slot(S_BETA), slot(S_GAMMA), u, n, p->tmp_n[0], p->tmp_n[1]);
+        LAUNCH1D(dev::batch_inverse_kernel, (n + dev::INV_CHUNK - 1) / dev::INV_CHUNK, 128, p->tmp_n[1], n);
+        LAUNCH1D(dev::mul_arrays_kernel, n, 256, p->tmp_n[0], p->tmp_n[1], n, p->tmp_n[2]);
+        H2A_TRY(scan_mul(ctx, p->tmp_n[2], n, p->totals));
+        H2A_TRY(upload_fr(ctx, slot(S_Z0), hh::fr_one()));
+        LAUNCH1D(dev::shift_scale_kernel, n, 256, p->tmp_n[2], slot(S_Z0), n, l.z.lag);
+        H2A_CUDA(ctx, cudaMemcpyAsync(l.z.lag + 32ull * (n - bf), bl_lookup_z[li], 32ull * bf, cudaMemcpyHostToDevice, st));
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g_lagrange, l.z.lag, n, cm));
+        write_point(cm);
+    }
+    steps.mark("lookup grand products");
+    H2A_CUDA(ctx, cudaMemcpyAsync(p->random_coef, bl, 32ull * n, cudaMemcpyHostToDevice, st));   // src/vanishing.rs:54-75
+    {
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g, p->random_coef, n, cm));
+        write_point(cm);                                                           // :419-421
+    }
+    hh::Fr y = tr.squeeze();                                                       // :423
+
+    // coefficient and extended forms of everything the quotient touches
+    for (auto& q : p->advice) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
+    for (auto& q : p->instance) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
+    for (auto& q : p->pz) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
+    for (auto& l : p->lk)
+        for (Poly3* q : {&l.pa, &l.ps, &l.z}) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
+    steps.mark("ifft + coset fft of committed columns");
+    hh::fr_store(p->qargs.beta, beta); hh::fr_store(p->qargs.gamma, gamma); hh::fr_store(p->qargs.theta, theta); hh::fr_store(p->qargs.y, y);
+    H2A_CUDA(ctx, cudaMemcpyAsync(p->d_qargs, &p->qargs, sizeof(QuotientArgs), cudaMemcpyHostToDevice, st));
+    LAUNCH1D(dev::quotient_kernel, m, 128, p->d_qargs);
+    {   // extended_to_coeff, then h is cut into quotient_poly_degree pieces of n coefficients
+        uint8_t w[32];
+        hh::fr_store(w, hh::fr_root_of_unity((int)s.ext_k));
+        H2A_TRY(h2a_ntt_run(ctx, p->h_ext, m, p->h_ext, p->h_coef, s.ext_k, w, 1, p->coset));
+    }
+    steps.mark("quotient evaluation + extended_to_coeff");
+    for (uint32_t i = 0; i < s.qdeg; i++) {                                        // :427-434, src/vanishing.rs:77-106
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g, p->h_coef + 32ull * n * i, n, cm));
+        write_point(cm);
+    }
+    steps.mark("h commitments");
+    hh::Fr x = tr.squeeze();                                                       // :436
+
+    // ---- evaluations: all requested first, fetched with one copy
+    std::map<int32_t, int> point_slot;                                            // rotation -> slot of x * omega^rot
+    auto point_of = [&](int32_t rot) -> int {
+        auto it = point_slot.find(rot);
+        if (it != point_slot.end()) return it->second;
+        int sl = 8 + (int)point_slot.size();
+        point_slot[rot] = sl;
+        return sl;
+    };
+    struct Ev { const uint8_t* coef; int32_t rot; };
+    std::vector<Ev> evs;
+    for (auto& q : s.iq) evs.push_back({p->instance[q.col].coef, q.rot});
+    for (auto& q : s.aq) evs.push_back({p->advice[q.col].coef, q.rot});
+    for (auto& q : s.fq) evs.push_back({p->fixed[q.col].coef, q.rot});
+    evs.push_back({p->random_coef, 0});
+    for (auto& q : p->sigma) evs.push_back({q.coef, 0});
+    for (uint32_t i = 0; i < s.n_chunks; i++) {
+        evs.push_back({p->pz[i].coef, 0});
+        evs.push_back({p->pz[i].coef, 1});
+        if (i + 1 < s.n_chunks) evs.push_back({p->pz[i].coef, s.last_rot});
+    }
+    for (auto& l : p->lk) {
+        evs.push_back({l.z.coef, 0}); evs.push_back({l.z.coef, 1}); evs.push_back({l.pa.coef, 0}); evs.push_back({l.pa.coef, -1}); evs.push_back({l.ps.coef, 0});
+    }
+    if (S_EVAL0 + evs.size() + 8 > 1000) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: too many evaluations");
+    for (auto& e : evs) point_of(e.rot);
+    point_of(0);
+    for (auto& kv : point_slot) H2A_TRY(upload_fr(ctx, slot(kv.second), rotate_point(s, x, kv.first)));
+    for (size_t i = 0; i < evs.size(); i++) H2A_TRY(eval_poly(ctx, p, evs[i].coef, n, slot(point_slot[evs[i].rot]), slot(S_EVAL0 + (int)i)));
+    std::vector<uint8_t> evb(32 * evs.size());
+    H2A_CUDA(ctx, cudaMemcpyAsync(evb.data(), slot(S_EVAL0), evb.size(), cudaMemcpyDeviceToHost, st));
+    H2A_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<hh::Fr> evals(evs.size());
+    for (size_t i = 0; i < evs.size(); i++) { evals[i] = hh::fr_load(evb.data() + 32 * i); write_scalar(evals[i]); }   // :438-510
+    steps.mark("evaluations");
+    hh::Fr v = tr.squeeze();                                                       // :718
+    (void)tr.squeeze();                                                            // :719 u (not used by the prover)
+    H2A_TRY(upload_fr(ctx, slot(S_V), v));
+
+    // ---- multi-open: queries in the verifier's order (:654-715), grouped by rotation (src/multiopen.rs:19-45)
+    // H = sum_i (x^n)^i h_i as a polynomial of degree < n (Horner from the top piece)
+    hh::Fr xn = x;
+    for (uint32_t i = 0; i < s.k; i++) xn = hh::sqr(xn);
+    H2A_TRY(upload_fr(ctx, slot(S_Y), xn));
+    uint8_t* h_poly = p->tmp_n[0];
+    for (int i = (int)s.qdeg - 1; i >= 0; i--)
+        LAUNCH1D(dev::axpy_kernel, n, 256, h_poly, p->h_coef + 32ull * n * i, slot(S_Y), n, i == (int)s.qdeg - 1);
+    struct MQ { const uint8_t* coef; int32_t rot; };
+    std::vector<MQ> mq;
+    for (auto& q : s.iq) mq.push_back({p->instance[q.col].coef, q.rot});
+    for (auto& q : s.aq) mq.push_back({p->advice[q.col].coef, q.rot});
+    for (uint32_t i = 0; i < s.n_chunks; i++) { mq.push_back({p->pz[i].coef, 0}); mq.push_back({p->pz[i].coef, 1}); }
+    for (int i = (int)s.n_chunks - 2; i >= 0; i--) mq.push_back({p->pz[i].coef, s.last_rot});
+    for (auto& l : p->lk) { mq.push_back({l.z.coef, 0}); mq.push_back({l.pa.coef, 0}); mq.push_back({l.ps.coef, 0}); mq.push_back({l.pa.coef, -1}); mq.push_back({l.z.coef, 1}); }
+    for (auto& q : s.fq) mq.push_back({p->fixed[q.col].coef, q.rot});
+    for (auto& q : p->sigma) mq.push_back({q.coef, 0});
+    mq.push_back({h_poly, 0});
+    mq.push_back({p->random_coef, 0});
+    std::map<int32_t, std::vector<size_t>> sets;
+    for (size_t i = 0; i < mq.size(); i++) sets[mq[i].rot].push_back(i);
+    const uint32_t nchunks = (n + dev::HORNER_L - 1) / dev::HORNER_L;
+    for (auto& kv : sets) {                                                        // src/multiopen.rs:344-395 (prover mirror)
+        uint8_t* batch = p->tmp_n[1];
+        bool first = true;
+        for (size_t qi : kv.second) { LAUNCH1D(dev::axpy_kernel, n, 256, batch, mq[qi].coef, slot(S_V), n, first ? 1 : 0); first = false; }
+        if (!point_slot.count(kv.first)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: rotation without evaluation point");
+        const uint8_t* d_z = slot(point_slot[kv.first]);
+        LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, batch, n, d_z, p->chunks);
+        dev::kate_carry_kernel<<<1, 128, 0, st>>>(p->chunks, nchunks, d_z, p->carries);
+        H2A_LAUNCH_CHECK(ctx);
+        LAUNCH1D(dev::kate_quotient_kernel, nchunks, 128, batch, n, d_z, p->carries, p->tmp_n[2]);
+        hh::PointA cm;
+        H2A_TRY(commit(ctx, p->g, p->tmp_n[2], n, cm));
+        write_point(cm);                                                           // src/multiopen.rs:392
+    }
+    steps.mark("multiopen witnesses");
+    *proof_len = pos;
+
+    H2A_CUDA(ctx, cudaStreamSynchronize(st));
+    p->phase_ms.clear();
+    ctx->prove_phase_names.clear();
+    for (size_t i = 1; i < steps.ev.size(); i++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, steps.ev[i - 1], steps.ev[i]);
+        p->phase_ms.push_back(ms);
+        ctx->prove_phase_names.push_back(steps.names[i]);
+    }
+    for (cudaEvent_t e : steps.ev) cudaEventDestroy(e);
+    return H2A_OK;
+}
+
+// Per-phase times (ms) of the last h2a_create_proof on this circuit; returns the count written.
+int h2a_prove_phase_ms(h2a_ctx* ctx, const h2a_circuit* c, float* ms, int cap) {
+    if (!ctx || !c || !c->prover || !ms) return H2A_ERR_INVALID;
+    int k = std::min<int>(cap, (int)c->prover->phase_ms.size());
+    for (int i = 0; i < k; i++) ms[i] = c->prover->phase_ms[i];
+    return k;
+}
+const char* h2a_prove_phase_name(const h2a_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= (int)ctx->prove_phase_names.size()) return "";
+    return ctx->prove_phase_names[i];
+}
+
+}  // extern "C"

@@ -159,6 +159,34 @@ int h2a_verify_proof_batch(h2a_ctx* ctx, const h2a_circuit* circuit, size_t n_pr
                            const uint8_t* instance_commitments /* n_proofs*n_instance*64 */, const uint8_t* const* proofs,
                            const size_t* proof_lens, uint8_t* out_efwzw /* n_proofs*256 */);
 
+/* ---- prover pipeline ----------------------------------------------------------------------------
+ * Replaces halo2 `plonk::create_proof(&params, &pk, &[circuit], &[&[&public_inputs]], &mut transcript)` as
+ * called at examples/simple-example.rs:606-613 and :702-709, for a circuit given by its shape, its proving-key
+ * columns and its (already synthesised and blinded) witness columns.  The proof bytes follow the wire order
+ * `VerifierChip::_verify_proof` reads (src/verifier.rs:341-510, src/multiopen.rs:392).
+ *   h2a_circuit_set_keys: `g` = Params.g, `g_lagrange` = Params.g_lagrange (resident handles, not owned);
+ *     fixed_values = n_fixed columns of n elements, sigmas = n_perm permutation columns of n elements
+ *     (keygen_pk output); commits them (so the verifying key is set as well) and keeps their coefficient and
+ *     extended-coset forms on the device.  coset_shift = the generator of the evaluation coset (halo2: ZETA).
+ *   h2a_create_proof: instance_cols / advice_cols = column-major, n elements each, advice already blinded.
+ *     blinds = the prover's randomness, drawn by the caller, h2a_blinds_len(circuit) elements:
+ *       per lookup: A' tail (bf+1), S' tail (bf+1), Z tail (bf); per permutation chunk: Z tail (bf);
+ *       then the n coefficients of the random polynomial.
+ *     Writes h2a_proof_len(circuit) bytes and the instance commitments.
+ * H2A_ERR_INVALID when a lookup input is absent from its table (the only witness error the pipeline detects). */
+int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* circuit, const h2a_bases* g, const h2a_bases* g_lagrange,
+                         const uint8_t* fixed_values, const uint8_t* sigmas, const uint8_t vk_hash[32],
+                         const uint8_t coset_shift[32]);
+int h2a_circuit_get_vk(h2a_ctx* ctx, const h2a_circuit* circuit, uint8_t* fixed_commitments, uint8_t* sigma_commitments);
+size_t h2a_blinds_len(const h2a_circuit* circuit);
+size_t h2a_proof_len(const h2a_circuit* circuit);
+int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* circuit, const uint8_t* instance_cols, const uint8_t* advice_cols,
+                     const uint8_t* blinds, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
+                     uint8_t* instance_commitments_out /* n_instance*64, may be NULL */);
+/* Per-phase device times (ms) of the last h2a_create_proof; returns the number of phases written. */
+int h2a_prove_phase_ms(h2a_ctx* ctx, const h2a_circuit* circuit, float* ms, int cap);
+const char* h2a_prove_phase_name(const h2a_ctx* ctx, int index);
+
 /* Blake2b transcript with Challenge255 (src/transcript.rs:58,72,105-107,122-124). */
 typedef struct h2a_transcript h2a_transcript;
 h2a_transcript* h2a_transcript_new(void);

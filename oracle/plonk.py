@@ -138,6 +138,21 @@ def BL_PERM_Z(i): return 1000 + i
 BL_RANDOM_POLY = 5000
 
 
+def blinds_buffer(shape, seed):
+    """The prover's randomness in the layout of include/h2agg.h `h2a_create_proof` (canonical integers)."""
+    n, u, bf = shape.n, shape.usable, shape.bf
+    out = []
+    for li in range(len(shape.lookups)):
+        out += [blind(seed, BL_LOOKUP_A(li), i) for i in range(n - u)]
+        out += [blind(seed, BL_LOOKUP_S(li), i) for i in range(n - u)]
+        out += [blind(seed, BL_LOOKUP_Z(li), i) for i in range(bf)]
+    cl = shape.chunk_len
+    for ci in range((len(shape.perm_columns) + cl - 1) // cl):
+        out += [blind(seed, BL_PERM_Z(ci), i) for i in range(bf)]
+    out += [blind(seed, BL_RANDOM_POLY, i) for i in range(n)]
+    return out
+
+
 class Params:
     """KZG setup for tests: g[i] = [s^i]G, g_lagrange[i] = [L_i(s)]G.  `s` is kept so the
     final pairing equation can be checked as a discrete-log relation in G1."""

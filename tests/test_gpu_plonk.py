@@ -80,3 +80,46 @@ def test_verifier_glue_batch_of_64(ctx, orc):
         assert bytes(got[i]) == bytes(efwzw_bytes(wants[i % 8])), i
     assert all(pk.pairing_relation_holds(w, params.s) for w in wants)
     circ.free()
+
+
+def cols_bytes(cols):
+    return np.frombuffer(b"".join(pm.fr_mont_bytes(v) for col in cols for v in col), dtype=np.uint8)
+
+
+def prove_with_library(ctx, orc, c, params, keys, seed):
+    shape = c["shape"]
+    g, gl = ctx.upload_bases(params.g), ctx.upload_bases(params.g_lagrange)
+    circ = h2a.Circuit(ctx, shape, frs_bytes(shape.constants))
+    circ.set_keys(g, gl, cols_bytes(c["fixed"]), cols_bytes(keys.sigmas), frs_bytes([keys.vk_hash]), frs_bytes([shape.coset_shift]))
+    proof, inst = circ.prove(cols_bytes(c["instance"]), cols_bytes(c["advice"]), frs_bytes(pk.blinds_buffer(shape, seed)))
+    return circ, proof, inst, (g, gl)
+
+
+@pytest.mark.parametrize("which,k", [("my_circuit", 6), ("wide", 6), ("my_circuit", 9), ("my_circuit", 12)])
+def test_prover_writes_byte_identical_proofs(ctx, orc, which, k):
+    """Row a1: same transcript, same commitments, same evaluations, same witnesses -> identical bytes
+    (k = 9 is the reference's own sample size, examples/simple-example.rs:561; k = 12 takes the multi-pass NTT)."""
+    c = circuits.my_circuit(k=k, table_bits=min(8, k - 2)) if which == "my_circuit" else circuits.wide_circuit(k=k)
+    if k > 9:
+        pytest.skip("oracle prover too slow beyond k=9; covered by test_large_proof_verifies")
+    params, keys = circuits.setup(orc, c)
+    want, want_inst = pk.create_proof(orc, params, c["shape"], keys, c["instance"], c["advice"], seed=5)
+    circ, proof, inst, handles = prove_with_library(ctx, orc, c, params, keys, seed=5)
+    fc, sc = circ.get_vk(c["shape"].num_fixed, len(c["shape"].perm_columns))
+    assert bytes(fc) == bytes(pts_bytes(keys.fixed_commitments)) and bytes(sc) == bytes(pts_bytes(keys.sigma_commitments))
+    assert bytes(inst) == bytes(pts_bytes(want_inst))
+    assert len(proof) == len(want) == circ.proof_len()
+    if proof != want:
+        first = next(i for i in range(0, len(want), 32) if proof[i:i + 32] != want[i:i + 32])
+        raise AssertionError("proofs differ first at 32-byte item %d of %d" % (first // 32, len(want) // 32))
+    # and the library's own verifier glue accepts what it wrote
+    res = pk.verify_proof(c["shape"], keys.fixed_commitments, keys.sigma_commitments, keys.vk_hash, want_inst, proof)
+    assert bytes(circ.verify(inst, proof)) == bytes(efwzw_bytes(res)) and pk.pairing_relation_holds(res, params.s)
+    # a lookup input outside the table is reported, not silently proven
+    bad = [col[:] for col in c["advice"]]
+    bad[0][0] = 12345678
+    with pytest.raises(h2a.H2AError):
+        circ.prove(cols_bytes(c["instance"]), cols_bytes(bad), frs_bytes(pk.blinds_buffer(c["shape"], 5)))
+    circ.free()
+    for h in handles:
+        h.free()
