@@ -189,6 +189,12 @@ class Context:
         self._check(self.lib.h2a_bases_from_device(self.h, ctypes.c_void_p(dev), c_sz(n), ctypes.byref(h)))
         return Bases(self, h)
 
+    def kzg_setup(self, k, s):
+        """Setup::<Bn256>::new(k, .) for the secret s: (g, g_lagrange) resident handles."""
+        g, gl = ctypes.c_void_p(), ctypes.c_void_p()
+        self._check(self.lib.h2a_kzg_setup(self.h, ctypes.c_uint32(k), _ptr(_bytes(s)), ctypes.byref(g), ctypes.byref(gl)))
+        return Bases(self, g), Bases(self, gl)
+
     def set_msm_window(self, c):
         self._check(self.lib.h2a_msm_set_window(self.h, int(c)))
 
@@ -285,7 +291,7 @@ class Context:
         return out
 
     # ---- test hooks
-    FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5}
+    FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "to_mont": 6, "from_mont": 7}
 
     def field_op(self, field, op, a, b=None):
         a = _bytes(a)
@@ -422,6 +428,11 @@ class Bases:
 
     def __len__(self):
         return int(self.ctx.lib.h2a_bases_len(self.h))
+
+    def download(self):
+        out = np.zeros(64 * len(self), np.uint8)
+        self.ctx._check(self.ctx.lib.h2a_bases_download(self.ctx.h, self.h, _ptr(out)))
+        return out
 
     def precompute(self, window_bits=-1):
         """Build the window tables 2^(window_bits*w) * P_i (h2a_bases_precompute); 0 drops them."""

@@ -57,6 +57,13 @@ int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases) {
     return H2A_OK;
 }
 size_t h2a_bases_len(const h2a_bases* bases) { return bases ? bases->n : 0; }
+int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy) {
+    if (!ctx || !bases || (!out_affine_xy && bases->n)) return H2A_ERR_INVALID;
+    if (!bases->n) return H2A_OK;
+    H2A_CUDA(ctx, cudaMemcpyAsync(out_affine_xy, bases->d, 64 * bases->n, cudaMemcpyDeviceToHost, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
 int h2a_bases_precompute(h2a_ctx* ctx, h2a_bases* bases, int window_bits) {
     if (!ctx || !bases) return H2A_ERR_INVALID;
     if (window_bits == 0) {  // drop the tables

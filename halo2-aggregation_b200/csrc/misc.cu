@@ -135,6 +135,8 @@ __global__ void field_op_kernel(int op, const uint8_t* a, const uint8_t* b, uint
         case 2: r = x * y; break;
         case 3: r = x.sqr(); break;
         case 4: r = x.inv(); break;
+        case 6: r = x.to_mont(); break;
+        case 7: r = x.from_mont(); break;
         default: r = x.neg(); break;
     }
     r.store(out + 32 * i);
@@ -333,7 +335,7 @@ static int run_elementwise(h2a_ctx* ctx, int kind, int field, int op, const uint
     return H2A_OK;
 }
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
-    if (field < 0 || field > 1 || op < 0 || op > 5) return H2A_ERR_INVALID;
+    if (field < 0 || field > 1 || op < 0 || op > 7) return H2A_ERR_INVALID;
     if (op <= 2 && !b) return H2A_ERR_INVALID;
     return run_elementwise(ctx, 0, field, op, a, op <= 2 ? b : nullptr, out, n, 32);
 }

@@ -350,6 +350,50 @@ __global__ void __launch_bounds__(128) kate_quotient_kernel(const uint8_t* p, ui
     }
 }
 
+// ---- KZG setup: Lagrange-basis scalars and fixed-base multiplication
+// den[i] = n * (s - omega^i)
+__global__ void lagrange_den_kernel(const uint8_t* omega_pows, const uint8_t* s_, const uint8_t* n_, uint32_t n, uint8_t* den) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) (Fr::load(n_) * (Fr::load(s_) - ld(omega_pows, i))).store(den + 32ull * i);
+}
+// out[i] = omega^i * (s^n - 1) * den_inv[i]
+__global__ void lagrange_num_kernel(const uint8_t* omega_pows, const uint8_t* snm1_, const uint8_t* den_inv, uint32_t n, uint8_t* out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) (ld(omega_pows, i) * Fr::load(snm1_) * ld(den_inv, i)).store(out + 32ull * i);
+}
+
+}  // namespace dev
+
+#include "curve.cuh"
+namespace dev {
+// out[i] = scalars[i] * G with a table of 2^j * G (affine): mixed additions only, one inversion per point
+__global__ void __launch_bounds__(128) fixed_base_mul_kernel(const uint8_t* table, const uint8_t* scalars, uint32_t n, uint8_t* out) {
+    __shared__ __align__(16) uint8_t tab[254 * 64];
+    for (uint32_t k = threadIdx.x; k < 254 * 4; k += blockDim.x) ((uint4*)tab)[k] = ((const uint4*)table)[k];
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr sc = ld(scalars, i).from_mont();
+    XYZZ acc = XYZZ::identity();
+#pragma unroll 1
+    for (int limb = 0; limb < 8; limb++) {
+        uint32_t w = sc.l[limb];  // limb index is the loop counter of a fully dynamic loop: local memory by design
+#pragma unroll 1
+        for (int b = 0; b < 32 && 32 * limb + b < 254; b++)
+            if ((w >> b) & 1) acc.add_affine(Affine::load(tab + 64 * (32 * limb + b)), false);
+    }
+    Affine o;
+    if (acc.is_identity()) {
+        o.x = Fq::zero();
+        o.y = Fq::zero();
+    } else {
+        Fq zi = acc.zzz.inv();
+        Fq zzi = (zi * acc.zz).sqr();
+        o.x = acc.x * zzi;
+        o.y = acc.y * zi;
+    }
+    o.store(out + 64ull * i);
+}
 }  // namespace dev
 
 // ====================================================================== host side
@@ -966,6 +1010,74 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         ctx->prove_phase_names.push_back(steps.names[i]);
     }
     for (cudaEvent_t e : steps.ev) cudaEventDestroy(e);
+    return H2A_OK;
+}
+
+// KZG setup with a caller-supplied secret: g[i] = [s^i] G, g_lagrange[i] = [L_i(s)] G, L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)).
+int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s_[32], h2a_bases** out_g, h2a_bases** out_g_lagrange) {
+    if (!ctx || !s_ || !out_g || !out_g_lagrange) return H2A_ERR_INVALID;
+    if (k < 1 || k > 26) H2A_FAIL(ctx, H2A_ERR_INVALID, "kzg_setup: k=%u not in 1..26", k);
+    const uint32_t n = 1u << k;
+    cudaStream_t st = ctx->stream;
+    // table of 2^j * G
+    std::vector<uint8_t> tab(254 * 64);
+    {
+        hh::PointX cur = hh::px_from_affine(hh::PointA{hh::fq_one(), hh::Fq{hh::el_from_u64(2, hh::MOD_Q)}});
+        for (int j = 0; j < 254; j++) {
+            hh::affine_store(tab.data() + 64 * j, hh::px_to_affine(cur));
+            cur = hh::px_dbl(cur);
+        }
+    }
+    uint8_t *d_tab = nullptr, *d_sc = nullptr, *d_w = nullptr, *d_den = nullptr, *d_small = nullptr, *d_g = nullptr, *d_gl = nullptr;
+    auto cleanup = [&]() { for (uint8_t* q : {d_tab, d_sc, d_w, d_den, d_small}) if (q) cudaFree(q); };
+#define SETUP_CUDA(call)                                                                    \
+    do {                                                                                    \
+        cudaError_t _e = (call);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            cleanup();                                                                      \
+            if (d_g) cudaFree(d_g);                                                         \
+            if (d_gl) cudaFree(d_gl);                                                       \
+            H2A_FAIL(ctx, H2A_ERR_CUDA, "kzg_setup: %s -> %s", #call, cudaGetErrorString(_e)); \
+        }                                                                                   \
+    } while (0)
+    SETUP_CUDA(cudaMalloc(&d_tab, tab.size()));
+    SETUP_CUDA(cudaMalloc(&d_sc, 32ull * n));
+    SETUP_CUDA(cudaMalloc(&d_w, 32ull * n));
+    SETUP_CUDA(cudaMalloc(&d_den, 32ull * n));
+    SETUP_CUDA(cudaMalloc(&d_small, 256));
+    SETUP_CUDA(cudaMalloc(&d_g, 64ull * n));
+    SETUP_CUDA(cudaMalloc(&d_gl, 64ull * n));
+    SETUP_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice, st));
+    hh::Fr s = hh::fr_load(s_), omega = hh::fr_root_of_unity((int)k), sn = s;
+    for (uint32_t i = 0; i < k; i++) sn = hh::sqr(sn);
+    uint8_t small[96], oneb[32], wb[32];
+    hh::fr_store(small, s);
+    hh::fr_store(small + 32, hh::fr_from_u64(n));
+    hh::fr_store(small + 64, sn - hh::fr_one());
+    hh::fr_store(oneb, hh::fr_one());
+    hh::fr_store(wb, omega);
+    SETUP_CUDA(cudaMemcpyAsync(d_small, small, 96, cudaMemcpyHostToDevice, st));
+    SETUP_CUDA(cudaStreamSynchronize(st));
+    int rc = h2a_pow_vector(ctx, s_, oneb, n, d_sc);                       // s^i
+    if (rc == H2A_OK) rc = h2a_pow_vector(ctx, wb, oneb, n, d_w);          // omega^i
+    if (rc != H2A_OK) { cleanup(); cudaFree(d_g); cudaFree(d_gl); return rc; }
+    const unsigned blocks = (n + 127) / 128;
+    dev::fixed_base_mul_kernel<<<blocks, 128, 0, st>>>(d_tab, d_sc, n, d_g);
+    ctx->launches++;
+    dev::lagrange_den_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_w, d_small, d_small + 32, n, d_den);
+    dev::batch_inverse_kernel<<<((n + dev::INV_CHUNK - 1) / dev::INV_CHUNK + 127) / 128, 128, 0, st>>>(d_den, n);
+    dev::lagrange_num_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_w, d_small + 64, d_den, n, d_sc);
+    dev::fixed_base_mul_kernel<<<blocks, 128, 0, st>>>(d_tab, d_sc, n, d_gl);
+    ctx->launches += 4;
+    SETUP_CUDA(cudaGetLastError());
+    SETUP_CUDA(cudaStreamSynchronize(st));
+#undef SETUP_CUDA
+    cleanup();
+    h2a_bases *bg = new h2a_bases(), *bl = new h2a_bases();
+    bg->d = d_g; bg->n = n; bg->owned = true;
+    bl->d = d_gl; bl->n = n; bl->owned = true;
+    *out_g = bg;
+    *out_g_lagrange = bl;
     return H2A_OK;
 }
 

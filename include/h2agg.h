@@ -183,6 +183,14 @@ size_t h2a_proof_len(const h2a_circuit* circuit);
 int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* circuit, const uint8_t* instance_cols, const uint8_t* advice_cols,
                      const uint8_t* blinds, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
                      uint8_t* instance_commitments_out /* n_instance*64, may be NULL */);
+/* KZG parameters on the device: g[i] = [s^i] G and g_lagrange[i] = [L_i(s)] G for i < 2^k, what
+ * `Setup::<Bn256>::new(k, rng)` builds (examples/simple-example.rs:589, :687) once `rng` has produced the
+ * secret `s` (an input here: how the dependency draws it from XorShiftRng is not visible from the reference).
+ * The Lagrange basis uses the closed form L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)) — fixed-base
+ * multiplications only, no group FFT.  Returns two resident handles (free with h2a_bases_free). */
+int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s[32], h2a_bases** out_g, h2a_bases** out_g_lagrange);
+/* Copy resident bases back to the host (n * 64 bytes), e.g. to write a params file. */
+int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy);
 /* Per-phase device times (ms) of the last h2a_create_proof; returns the number of phases written. */
 int h2a_prove_phase_ms(h2a_ctx* ctx, const h2a_circuit* circuit, float* ms, int cap);
 const char* h2a_prove_phase_name(const h2a_ctx* ctx, int index);
@@ -203,7 +211,8 @@ int h2a_gen_scalars_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, voi
 int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out /* n*64 */);
 
 /* ---- test / measurement hooks ---------------------------------------------------------- */
-/* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inv 5 neg. */
+/* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inv 5 neg
+ * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer. */
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);

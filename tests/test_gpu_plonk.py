@@ -95,13 +95,11 @@ def prove_with_library(ctx, orc, c, params, keys, seed):
     return circ, proof, inst, (g, gl)
 
 
-@pytest.mark.parametrize("which,k", [("my_circuit", 6), ("wide", 6), ("my_circuit", 9), ("my_circuit", 12)])
+@pytest.mark.parametrize("which,k", [("my_circuit", 6), ("wide", 6), ("my_circuit", 9)])
 def test_prover_writes_byte_identical_proofs(ctx, orc, which, k):
     """Row a1: same transcript, same commitments, same evaluations, same witnesses -> identical bytes
-    (k = 9 is the reference's own sample size, examples/simple-example.rs:561; k = 12 takes the multi-pass NTT)."""
+    (k = 9 is the reference's own sample size, examples/simple-example.rs:561)."""
     c = circuits.my_circuit(k=k, table_bits=min(8, k - 2)) if which == "my_circuit" else circuits.wide_circuit(k=k)
-    if k > 9:
-        pytest.skip("oracle prover too slow beyond k=9; covered by test_large_proof_verifies")
     params, keys = circuits.setup(orc, c)
     want, want_inst = pk.create_proof(orc, params, c["shape"], keys, c["instance"], c["advice"], seed=5)
     circ, proof, inst, handles = prove_with_library(ctx, orc, c, params, keys, seed=5)
@@ -123,3 +121,47 @@ def test_prover_writes_byte_identical_proofs(ctx, orc, which, k):
     circ.free()
     for h in handles:
         h.free()
+
+
+def test_kzg_setup_matches_oracle(ctx, orc):
+    """Row a10: Setup::new for a given secret — g and g_lagrange equal the oracle's, point for point."""
+    s = 0x1234567890abcdef1234567890abcdef
+    for k in (1, 6):
+        params = pk.Params(orc, k, s)
+        g, gl = ctx.kzg_setup(k, frs_bytes([s]))
+        assert bytes(g.download()) == bytes(params.g)
+        assert bytes(gl.download()) == bytes(params.g_lagrange)
+        g.free(); gl.free()
+    # commit_lagrange of the constant-one column is [1] G: sum of the Lagrange basis
+    g, gl = ctx.kzg_setup(10, frs_bytes([s]))
+    ones = frs_bytes([1] * 1024)
+    assert pm.affine_from_bytes(ctx.msm(gl, ones)) == pm.G1
+    g.free(); gl.free()
+
+
+@pytest.mark.parametrize("k", [11, 14])
+def test_large_proof_verifies(ctx, orc, k):
+    """Beyond the oracle prover's reach: prove on the device with device-generated parameters, then check the proof
+    with the oracle verifier and the pairing relation (multi-pass NTT, recursive scans, chunked Kate division)."""
+    s = 0x0badc0ffee0ddf00d1234567890abcdef
+    c = circuits.my_circuit(k=k, table_bits=8, a=251, b=97, constant=4242)
+    shape = c["shape"]
+    g, gl = ctx.kzg_setup(k, frs_bytes([s]))
+    sigmas = pk.build_sigmas(shape, c["cycles"])
+    circ = h2a.Circuit(ctx, shape, frs_bytes(shape.constants))
+    circ.set_keys(g, gl, cols_bytes(c["fixed"]), cols_bytes(sigmas), frs_bytes([77]), frs_bytes([shape.coset_shift]))
+    proof, inst = circ.prove(cols_bytes(c["instance"]), cols_bytes(c["advice"]), frs_bytes(pk.blinds_buffer(shape, 9)))
+    fc, sc = circ.get_vk(shape.num_fixed, len(shape.perm_columns))
+    to_pts = lambda b: [pm.affine_from_bytes(b[64 * i:64 * i + 64]) for i in range(len(b) // 64)]
+    res = pk.verify_proof(shape, to_pts(fc), to_pts(sc), 77, to_pts(inst), proof)
+    assert pk.pairing_relation_holds(res, s)
+    assert bytes(circ.verify(inst, proof)) == bytes(efwzw_bytes(res))
+    phases = circ.prove_phases()
+    assert len(phases) >= 8 and all(ms >= 0 for _, ms in phases)
+    # a wrong witness (broken product) still yields a proof, which must NOT verify
+    bad = [col[:] for col in c["advice"]]
+    bad[0][4] = (bad[0][4] + 1) % pm.R
+    proof2, inst2 = circ.prove(cols_bytes(c["instance"]), cols_bytes(bad), frs_bytes(pk.blinds_buffer(shape, 9)))
+    res2 = pk.verify_proof(shape, to_pts(fc), to_pts(sc), 77, to_pts(inst2), proof2)
+    assert not pk.pairing_relation_holds(res2, s)
+    circ.free(); g.free(); gl.free()
