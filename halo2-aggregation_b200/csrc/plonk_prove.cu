@@ -9,7 +9,8 @@
 //
 // Everything data-parallel runs in kernels of this file (expression evaluation over rows, grand-product
 // prefix scans with batch inversion, quotient evaluation, Horner evaluation, v-combination, Kate division);
-// the host keeps the Blake2b transcript and, for now, the lookup permutation (a sort).
+// the lookup permutation (bitonic sort of 256-bit keys + run matching + compaction); the host keeps only the
+// Blake2b transcript.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -350,6 +351,146 @@ __global__ void __launch_bounds__(128) kate_quotient_kernel(const uint8_t* p, ui
     }
 }
 
+// ---- lookup permutation on the device (halo2 `permute_expression_pair`, src/lookup.rs:49-79 reads its output)
+// keys are canonical 256-bit integers so that their order is the numeric order of the field elements
+__device__ __forceinline__ bool key_less(const Fr& a, const Fr& b) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (a.l[i] != b.l[i]) return a.l[i] < b.l[i];
+    }
+    return false;
+}
+__global__ void lookup_keys_kernel(const uint8_t* src, uint32_t u, uint32_t n, uint8_t* keys) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr k;
+    if (i < u) k = ld(src, i).from_mont();
+    else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) k.l[j] = 0xffffffffu;  // sentinel above every field element
+    }
+    k.store(keys + 32ull * i);
+}
+__global__ void bitonic_step_kernel(uint8_t* keys, uint32_t n, uint32_t j, uint32_t kk) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t p = i ^ j;
+    if (i >= n || p <= i) return;
+    Fr a = ld(keys, i), b = ld(keys, p);
+    const bool up = (i & kk) == 0;
+    if (key_less(b, a) == up) {
+        b.store(keys + 32ull * i);
+        a.store(keys + 32ull * p);
+    }
+}
+// shared-memory tail of a bitonic stage: all steps with j < 1024 of stage kk in one launch (tile of 2048 keys)
+__global__ void __launch_bounds__(1024) bitonic_tail_kernel(uint8_t* keys, uint32_t n, uint32_t j_start, uint32_t kk) {
+    extern __shared__ uint4 sh4[];
+    uint4* lo = sh4;
+    uint4* hi = sh4 + 2048;
+    const uint32_t base = blockIdx.x * 2048;
+    for (uint32_t t = threadIdx.x; t < 2048; t += 1024) {
+        const uint4* g = (const uint4*)(keys + 32ull * (base + t));
+        lo[t] = g[0];
+        hi[t] = g[1];
+    }
+    __syncthreads();
+    for (uint32_t j = j_start; j > 0; j >>= 1) {
+        const uint32_t t = threadIdx.x;
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // element with bit j clear
+        const uint32_t p = i | j;
+        Fr a, b;
+        uint4 x = lo[i], y = hi[i];
+        a.l[0] = x.x; a.l[1] = x.y; a.l[2] = x.z; a.l[3] = x.w; a.l[4] = y.x; a.l[5] = y.y; a.l[6] = y.z; a.l[7] = y.w;
+        x = lo[p]; y = hi[p];
+        b.l[0] = x.x; b.l[1] = x.y; b.l[2] = x.z; b.l[3] = x.w; b.l[4] = y.x; b.l[5] = y.y; b.l[6] = y.z; b.l[7] = y.w;
+        const bool up = ((base + i) & kk) == 0;
+        if (key_less(b, a) == up) {
+            lo[i] = make_uint4(b.l[0], b.l[1], b.l[2], b.l[3]); hi[i] = make_uint4(b.l[4], b.l[5], b.l[6], b.l[7]);
+            lo[p] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]); hi[p] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+        }
+        __syncthreads();
+    }
+    for (uint32_t t = threadIdx.x; t < 2048; t += 1024) {
+        uint4* g = (uint4*)(keys + 32ull * (base + t));
+        g[0] = lo[t];
+        g[1] = hi[t];
+    }
+}
+// first[row] = 1 when row starts a run of equal inputs; used[j] = 1 for the table entry matched to that run
+__global__ void lookup_match_kernel(const uint8_t* ka, const uint8_t* ks, uint32_t u, uint32_t* rep, uint32_t* unused, uint32_t* err) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= u) return;
+    Fr a = ld(ka, row);
+    bool first = row == 0;
+    if (!first) {
+        Fr prev = ld(ka, row - 1);
+        first = !(prev == a);
+    }
+    rep[row] = first ? 0u : 1u;
+    if (!first) return;
+    uint32_t lo = 0, hi = u;  // lower_bound of a in ks[0..u)
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (key_less(ld(ks, mid), a)) lo = mid + 1; else hi = mid;
+    }
+    if (lo < u && ld(ks, lo) == a) unused[lo] = 0u;   // unused[] starts as all ones
+    else atomicExch(err, 1u);
+}
+__global__ void fill_u32_kernel(uint32_t* a, uint32_t n, uint32_t v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+// exclusive scan of u32 flags, tiles of 2048: sums, single-block scan of the sums, apply
+__global__ void __launch_bounds__(256) u32_tile_sums_kernel(const uint32_t* a, uint32_t n, uint32_t* sums) {
+    __shared__ uint32_t sh[256];
+    uint32_t base = blockIdx.x * 2048 + threadIdx.x * 8, s = 0;
+    for (int k = 0; k < 8; k++) s += (base + k < n) ? a[base + k] : 0u;
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 128; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[blockIdx.x] = sh[0];
+}
+__global__ void u32_scan_sums_kernel(uint32_t* sums, uint32_t tiles, uint32_t* total) {  // one thread: tiles <= 2^15
+    uint32_t run = 0;
+    for (uint32_t t = 0; t < tiles; t++) { uint32_t v = sums[t]; sums[t] = run; run += v; }
+    *total = run;
+}
+__global__ void __launch_bounds__(256) u32_tile_apply_kernel(const uint32_t* a, uint32_t n, const uint32_t* sums, uint32_t* out) {
+    __shared__ uint32_t sh[256];
+    uint32_t base = blockIdx.x * 2048 + threadIdx.x * 8, v[8], s = 0;
+    for (int k = 0; k < 8; k++) { v[k] = (base + k < n) ? a[base + k] : 0u; s += v[k]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {
+        uint32_t add = (int)threadIdx.x >= d ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += add;
+        __syncthreads();
+    }
+    uint32_t ex = sh[threadIdx.x] - s + sums[blockIdx.x];
+    for (int k = 0; k < 8; k++) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+}
+// leftover[rank] = k-th table entry that no input run consumed (ascending)
+__global__ void lookup_leftover_kernel(const uint8_t* ks, const uint32_t* unused, const uint32_t* rank, uint32_t u, uint8_t* leftover) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < u && unused[j]) ld(ks, j).store(leftover + 32ull * rank[j]);
+}
+// A' = sorted inputs; S' = the run's own value on first rows, left-over table entries on repeated rows, handed out
+// from the last repeated row backwards; both back in Montgomery form
+__global__ void lookup_assign_kernel(const uint8_t* ka, const uint8_t* leftover, const uint32_t* rep, const uint32_t* rep_rank,
+                                     const uint32_t* n_rep, uint32_t u, uint8_t* pa, uint8_t* ps) {
+    uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= u) return;
+    Fr a = ld(ka, row);
+    a.to_mont().store(pa + 32ull * row);
+    Fr s = a;
+    if (rep[row]) s = ld(leftover, *n_rep - 1u - rep_rank[row]);
+    s.to_mont().store(ps + 32ull * row);
+}
+
 // ---- KZG setup: Lagrange-basis scalars and fixed-base multiplication
 // den[i] = n * (s - omega^i)
 __global__ void lagrange_den_kernel(const uint8_t* omega_pows, const uint8_t* s_, const uint8_t* n_, uint32_t n, uint8_t* den) {
@@ -414,6 +555,7 @@ struct ProverState {
     uint8_t *tmp_n[4] = {nullptr, nullptr, nullptr, nullptr}, *tmp_m = nullptr;
     uint8_t *omega_pows = nullptr;                                        // omega^i, i < n
     uint8_t *chunks = nullptr, *carries = nullptr, *totals = nullptr, *small = nullptr;
+    uint32_t* u32buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // rep, unused, rep_rank, unused_rank, tile sums / counters
     DevBuf xtab;                                                          // g * omega_ext^i two-level
     uint8_t *vanish_inv = nullptr;
     uint32_t* code = nullptr;
@@ -507,53 +649,37 @@ int eval_poly(h2a_ctx* ctx, ProverState* p, const uint8_t* coef, uint32_t n, con
     return H2A_OK;
 }
 
-struct Raw256 {
-    uint64_t v[4];
-    bool operator<(const Raw256& o) const {
-        for (int i = 3; i >= 0; i--)
-            if (v[i] != o.v[i]) return v[i] < o.v[i];
-        return false;
+// ascending bitonic sort of n = 2^log_n 256-bit keys in place
+int bitonic_sort(h2a_ctx* ctx, uint8_t* keys, uint32_t n) {
+    static bool attr = false;
+    if (!attr) {
+        H2A_CUDA(ctx, cudaFuncSetAttribute(dev::bitonic_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        attr = true;
     }
-    bool operator==(const Raw256& o) const { return memcmp(v, o.v, 32) == 0; }
-};
-
-// halo2 `permute_expression_pair` on the usable rows: A' = sorted inputs; S' puts each distinct input's table
-// entry on the row of its first occurrence and the left-over table entries (ascending) on the repeated rows,
-// filled from the last repeated row backwards.  Host side for now.
-bool permute_lookup(const std::vector<uint8_t>& A, const std::vector<uint8_t>& S, uint32_t u, std::vector<uint8_t>& pa,
-                    std::vector<uint8_t>& ps) {
-    std::vector<Raw256> a(u), s(u);
-    for (uint32_t i = 0; i < u; i++) {
-        hh::fr_to_raw(hh::fr_load(A.data() + 32 * i), a[i].v);
-        hh::fr_to_raw(hh::fr_load(S.data() + 32 * i), s[i].v);
-    }
-    std::sort(a.begin(), a.end());
-    std::sort(s.begin(), s.end());
-    std::vector<char> used(u, 0), filled(u, 0);
-    std::vector<Raw256> out(u);
-    std::vector<uint32_t> repeated;
-    uint32_t j = 0;
-    for (uint32_t row = 0; row < u; row++) {
-        if (row == 0 || !(a[row] == a[row - 1])) {
-            while (j < u && s[j] < a[row]) j++;
-            if (j >= u || !(s[j] == a[row])) return false;  // input value absent from the table
-            used[j++] = 1;
-            out[row] = a[row];
-            filled[row] = 1;
+    for (uint32_t kk = 2; kk <= n; kk <<= 1) {
+        uint32_t j = kk >> 1;
+        for (; j >= 1024 && n >= 2048; j >>= 1) LAUNCH1D(dev::bitonic_step_kernel, n, 256, keys, n, j, kk);
+        if (n >= 2048) {
+            if (j) {
+                dev::bitonic_tail_kernel<<<n / 2048, 1024, 65536, ctx->stream>>>(keys, n, j, kk);
+                H2A_LAUNCH_CHECK(ctx);
+            }
         } else {
-            repeated.push_back(row);
+            for (; j > 0; j >>= 1) LAUNCH1D(dev::bitonic_step_kernel, n, 256, keys, n, j, kk);
         }
     }
-    size_t r = repeated.size();
-    for (uint32_t t = 0; t < u; t++)
-        if (!used[t]) out[repeated[--r]] = s[t];
-    pa.resize(32 * (size_t)u);
-    ps.resize(32 * (size_t)u);
-    for (uint32_t i = 0; i < u; i++) {
-        hh::fr_store(pa.data() + 32 * i, hh::fr_from_raw(a[i].v));
-        hh::fr_store(ps.data() + 32 * i, hh::fr_from_raw(out[i].v));
-    }
-    return true;
+    return H2A_OK;
+}
+
+int u32_exclusive_scan(h2a_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* sums, uint32_t* total) {
+    const uint32_t tiles = (n + 2047) / 2048;
+    dev::u32_tile_sums_kernel<<<tiles, 256, 0, ctx->stream>>>(in, n, sums);
+    H2A_LAUNCH_CHECK(ctx);
+    dev::u32_scan_sums_kernel<<<1, 1, 0, ctx->stream>>>(sums, tiles, total);
+    H2A_LAUNCH_CHECK(ctx);
+    dev::u32_tile_apply_kernel<<<tiles, 256, 0, ctx->stream>>>(in, n, sums, out);
+    H2A_LAUNCH_CHECK(ctx);
+    return H2A_OK;
 }
 
 void compress_point(const hh::PointA& p, uint8_t out[32]) {
@@ -608,7 +734,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     const size_t nl = s.lookups.size();
     const size_t n_arrays = 2 * (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * (2 + 6) + 1 + 4 + 1 + 8;
     const size_t m_arrays = (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * 3 + 3 + 2 + 1;
-    p->arena_bytes = n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
+    p->arena_bytes = 5 * (4ull * n + 8192) + n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
                      sizeof(EvalTables) + sizeof(QuotientArgs);
     H2A_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
     auto poly3 = [&]() { Poly3 q; q.lag = arena_take(p, 32ull * n); q.coef = arena_take(p, 32ull * n); q.ext = arena_take(p, 32ull * m); return q; };
@@ -635,6 +761,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     p->carries = arena_take(p, 32ull * (m / dev::HORNER_L + 64));
     p->totals = arena_take(p, 32ull * (n / dev::SCAN_TILE + 4096));
     p->small = arena_take(p, 32 * 1024);
+    for (int i = 0; i < 5; i++) p->u32buf[i] = (uint32_t*)arena_take(p, 4ull * n + 4096);
     p->vanish_inv = arena_take(p, 32ull * (m / n));
     p->code = (uint32_t*)arena_take(p, code.size() * 4 + 16);
     p->consts = arena_take(p, 32 * s.consts.size() + 32);
@@ -811,13 +938,27 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         ProverState::Lk& l = p->lk[li];
         LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_in_first[li], p->qargs.lk_in_cnt[li], slot(S_THETA), n, l.A);
         LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_tab_first[li], p->qargs.lk_tab_cnt[li], slot(S_THETA), n, l.S);
-        std::vector<uint8_t> A(32ull * u), S(32ull * u), pa, ps;
-        H2A_CUDA(ctx, cudaMemcpyAsync(A.data(), l.A, A.size(), cudaMemcpyDeviceToHost, st));
-        H2A_CUDA(ctx, cudaMemcpyAsync(S.data(), l.S, S.size(), cudaMemcpyDeviceToHost, st));
-        H2A_CUDA(ctx, cudaStreamSynchronize(st));
-        if (!permute_lookup(A, S, u, pa, ps)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: lookup %zu has an input value absent from its table", li);
-        H2A_CUDA(ctx, cudaMemcpyAsync(l.pa.lag, pa.data(), pa.size(), cudaMemcpyHostToDevice, st));
-        H2A_CUDA(ctx, cudaMemcpyAsync(l.ps.lag, ps.data(), ps.size(), cudaMemcpyHostToDevice, st));
+        {   // A' and S' on the device: sort both, match runs to table entries, hand out the left-overs
+            uint8_t *ka = p->tmp_n[0], *ks = p->tmp_n[1], *leftover = p->tmp_n[2];
+            uint32_t *rep = p->u32buf[0], *unused = p->u32buf[1], *rep_rank = p->u32buf[2], *unused_rank = p->u32buf[3];
+            uint32_t *sums = p->u32buf[4], *counters = p->u32buf[4] + (n / 2048 + 8);   // counters: [0] n_rep, [1] n_unused, [2] error
+            LAUNCH1D(dev::lookup_keys_kernel, n, 256, l.A, u, n, ka);
+            LAUNCH1D(dev::lookup_keys_kernel, n, 256, l.S, u, n, ks);
+            H2A_TRY(bitonic_sort(ctx, ka, n));
+            H2A_TRY(bitonic_sort(ctx, ks, n));
+            LAUNCH1D(dev::fill_u32_kernel, u, 256, unused, u, 1u);
+            H2A_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, st));
+            LAUNCH1D(dev::lookup_match_kernel, u, 128, ka, ks, u, rep, unused, counters + 2);
+            H2A_TRY(u32_exclusive_scan(ctx, rep, u, rep_rank, sums, counters + 0));
+            H2A_TRY(u32_exclusive_scan(ctx, unused, u, unused_rank, sums, counters + 1));
+            LAUNCH1D(dev::lookup_leftover_kernel, u, 256, ks, unused, unused_rank, u, leftover);
+            LAUNCH1D(dev::lookup_assign_kernel, u, 128, ka, leftover, rep, rep_rank, counters + 0, u, l.pa.lag, l.ps.lag);
+            uint32_t host_counters[4];
+            H2A_CUDA(ctx, cudaMemcpyAsync(host_counters, counters, 16, cudaMemcpyDeviceToHost, st));
+            H2A_CUDA(ctx, cudaStreamSynchronize(st));
+            if (host_counters[2] || host_counters[0] != host_counters[1])
+                H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: lookup %zu has an input value absent from its table", li);
+        }
         H2A_CUDA(ctx, cudaMemcpyAsync(l.pa.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
         bl += 32ull * (n - u);
         H2A_CUDA(ctx, cudaMemcpyAsync(l.ps.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
