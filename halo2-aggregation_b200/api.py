@@ -198,6 +198,9 @@ class Context:
     def set_msm_window(self, c):
         self._check(self.lib.h2a_msm_set_window(self.h, int(c)))
 
+    def set_msm_algorithm(self, algo):
+        self._check(self.lib.h2a_msm_set_algorithm(self.h, int(algo)))
+
     def msm(self, bases, scalars, offset=0):
         """best_multiexp over resident bases, host scalars.  Returns the 64-byte affine result."""
         scalars = _bytes(scalars)

@@ -83,6 +83,12 @@ int h2a_msm_set_window(h2a_ctx* ctx, int c) {
     return H2A_OK;
 }
 
+int h2a_msm_set_algorithm(h2a_ctx* ctx, int algo) {
+    if (!ctx || algo < 0 || algo > 1) return H2A_ERR_INVALID;
+    ctx->msm_algo = algo;
+    return H2A_OK;
+}
+
 int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
                    uint8_t out_affine[64]) {
     if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;

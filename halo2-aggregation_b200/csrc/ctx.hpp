@@ -26,6 +26,7 @@ struct h2a_ctx {
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
+    int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
     // profiling
     bool profiling = false;
@@ -36,7 +37,7 @@ struct h2a_ctx {
     std::vector<const char*> prove_phase_names;
 
     // MSM workspace
-    DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc;
+    DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc, aff_a, aff_b, aff_scratch, aff_u32;
     void* pinned = nullptr;  // small pinned staging area for results
     size_t pinned_cap = 0;
 

@@ -238,6 +238,8 @@ int h2a_init(h2a_ctx** out, int device) {
     }
     const char* env = getenv("H2A_MSM_WINDOW");
     if (env) ctx->msm_window_override = atoi(env);
+    env = getenv("H2A_MSM_ALGO");
+    if (env) ctx->msm_algo = atoi(env) ? 1 : 0;
     *out = ctx;
     return H2A_OK;
 }
@@ -247,7 +249,8 @@ int h2a_destroy(h2a_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->scalars, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->buckets, &ctx->segsums,
-                      &ctx->winsums, &ctx->heavy,   &ctx->misc,   &ctx->ntt_a,  &ctx->ntt_b};
+                      &ctx->winsums, &ctx->heavy,   &ctx->misc,   &ctx->ntt_a,  &ctx->ntt_b,  &ctx->aff_a, &ctx->aff_b,
+                      &ctx->aff_scratch, &ctx->aff_u32};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     h2a_ntt_free_tables(ctx);

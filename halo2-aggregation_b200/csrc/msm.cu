@@ -155,17 +155,19 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* t
     __syncthreads();
     return r;
 }
-__device__ __forceinline__ uint64_t pack_count(uint32_t cnt, uint32_t task_len) {
-    return (uint64_t)cnt | ((uint64_t)((cnt + task_len - 1) / task_len) << 32);
+// `pad` rounds a non-empty bucket's slot count up to a multiple of pad (a power of two; 1 = none)
+__device__ __forceinline__ uint64_t pack_count(uint32_t cnt, uint32_t task_len, uint32_t pad) {
+    uint32_t slots = (cnt + pad - 1u) & ~(pad - 1u);
+    return (uint64_t)slots | ((uint64_t)((cnt + task_len - 1) / task_len) << 32);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const uint32_t* __restrict__ data, uint32_t n,
-                                                                       uint32_t task_len,
+                                                                       uint32_t task_len, uint32_t pad,
                                                                        uint64_t* __restrict__ block_sums) {
     uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     uint64_t s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? pack_count(data[base + k], task_len) : 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) s += (base + k < n) ? pack_count(data[base + k], task_len, pad) : 0;
     __shared__ uint64_t total;
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint64_t* __rest
 // data[k] <- start of bucket k; task_off[k] <- first task of bucket k (task_off[n] = number of tasks);
 // buckets cut into more than one task are appended to multi_list.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __restrict__ data, uint32_t n,
-                                                                  uint32_t task_len,
+                                                                  uint32_t task_len, uint32_t pad,
                                                                   const uint64_t* __restrict__ block_sums,
                                                                   uint32_t* __restrict__ task_off,
                                                                   uint32_t* __restrict__ multi_list, uint32_t multi_cap,
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __re
     uint64_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n) ? pack_count(data[base + k], task_len) : 0;
+        v[k] = (base + k < n) ? pack_count(data[base + k], task_len, pad) : 0;
         s += v[k];
     }
     uint64_t ex = block_exclusive_scan(s, nullptr) + block_sums[blockIdx.x];
@@ -311,6 +313,152 @@ __global__ void __launch_bounds__(128) msm_merge_light_kernel(const uint32_t* __
     acc.store(partial + 128ull * t0);
 }
 
+// =====================================================================================================
+// Batched-affine accumulation (ctx->msm_algo == 1).  Every bucket's slice of the sorted entries is padded to a
+// multiple of 2^R slots (dummy entries = identity), so R rounds of a perfectly regular pairwise tree
+//     out[o] = in[2o] + in[2o+1]
+// never cross a bucket boundary and need no per-output lookup: round 0 gathers the bases through the entries,
+// later rounds stream the previous round's point array.  Additions are affine — lambda = (y2-y1)/(x2-x1),
+// 2M + 1S — and their inversions are shared by a two-level Montgomery trick: a forward kernel leaves per-thread
+// prefix products and one total per thread, a small kernel inverts the totals 64 at a time with one field
+// inversion each, a backward kernel finishes the additions: about 6 products per addition instead of the 10 of an
+// XYZZ mixed addition.  After R rounds a bucket is down to (padded size / 2^R) points, which the XYZZ task kernel
+// folds exactly as in the other algorithm (so skewed inputs keep their bounded per-thread work).
+constexpr int AFF_B = 32;  // outputs per thread; a warp owns 32 * AFF_B consecutive outputs, lane l takes l, l+32, ...
+
+// kind: 0 result = p1, 4 result = p2, 1 generic addition, 2 doubling, 3 cancellation (identity)
+__device__ __forceinline__ int pair_case(const Affine& p1, const Affine& p2, Fq& d) {
+    if (p2.is_identity()) { d = Fq::one(); return 0; }
+    if (p1.is_identity()) { d = Fq::one(); return 4; }
+    Fq dx = p2.x - p1.x;
+    if (!dx.is_zero()) { d = dx; return 1; }
+    Fq sy = p1.y + p2.y;
+    if (sy.is_zero()) { d = Fq::one(); return 3; }
+    d = p1.y.dbl();
+    return 2;
+}
+
+template <bool FIRST>
+__device__ __forceinline__ Affine load_input(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                             const uint8_t* __restrict__ in_pts, uint32_t i) {
+    if (FIRST) {
+        const uint32_t e = sorted[i];
+        Affine p;
+        if (e == 0xffffffffu) { p.x = Fq::zero(); p.y = Fq::zero(); return p; }   // padding slot
+        p = Affine::load(bases + 64ull * (e & 0x7fffffffu));
+        if ((e >> 31) && !p.is_identity()) p.y = p.y.neg();
+        return p;
+    }
+    return Affine::load(in_pts + 64ull * i);
+}
+
+// forward pass: prefix products of this thread's denominators (parked in the scratch, coalesced), chunk total out
+template <bool FIRST>
+__global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                          const uint8_t* __restrict__ in_pts, uint32_t n_out,
+                                                          uint8_t* __restrict__ scratch, uint8_t* __restrict__ totals) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t base_o = warp * 32u * AFF_B;
+    Fq run = Fq::one();
+    uint32_t o = base_o + lane;
+#pragma unroll 1
+    for (int j = 0; j < AFF_B && o < n_out; j++, o += 32u) {
+        Affine p1 = load_input<FIRST>(bases, sorted, in_pts, 2u * o), p2 = load_input<FIRST>(bases, sorted, in_pts, 2u * o + 1u);
+        Fq d;
+        pair_case(p1, p2, d);
+        run.store(scratch + 32ull * (((size_t)warp * AFF_B + j) * 32u + lane));
+        run = run * d;
+    }
+    run.store(totals + 32ull * t);
+}
+// in-place inversion of the chunk totals, 64 per thread with one field inversion (second level of Montgomery's trick)
+__global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restrict__ totals, uint32_t count) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lo = t * 64u;
+    if (lo >= count) return;
+    const uint32_t cnt = min(64u, count - lo);
+    Fq pre[64];
+    Fq run = Fq::one();
+    for (uint32_t q = 0; q < cnt; q++) {
+        pre[q] = run;
+        run = run * Fq::load(totals + 32ull * (lo + q));
+    }
+    Fq inv = run.inv();
+    for (uint32_t q = cnt; q-- > 0;) {
+        Fq v = Fq::load(totals + 32ull * (lo + q));
+        (inv * pre[q]).store(totals + 32ull * (lo + q));
+        inv = inv * v;
+    }
+}
+// backward pass: individual inverses from the inverted chunk total, finish the additions
+template <bool FIRST>
+__global__ void __launch_bounds__(128) aff_backward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                           const uint8_t* __restrict__ in_pts, uint32_t n_out,
+                                                           const uint8_t* __restrict__ scratch, const uint8_t* __restrict__ totals,
+                                                           uint8_t* __restrict__ out_pts) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t base_o = warp * 32u * AFF_B;
+    if (base_o + lane >= n_out) return;
+    const uint32_t cnt = min((uint32_t)AFF_B, (n_out - base_o - lane + 31u) / 32u);  // outputs of this lane
+    Fq inv = Fq::load(totals + 32ull * t);
+    uint32_t o = base_o + lane + 32u * (cnt - 1u);
+#pragma unroll 1
+    for (int j = (int)cnt - 1; j >= 0; j--, o -= 32u) {
+        Affine p1 = load_input<FIRST>(bases, sorted, in_pts, 2u * o), p2 = load_input<FIRST>(bases, sorted, in_pts, 2u * o + 1u);
+        Fq d;
+        const int kind = pair_case(p1, p2, d);
+        Affine r = p1;
+        if (kind == 4) r = p2;
+        else if (kind == 3) { r.x = Fq::zero(); r.y = Fq::zero(); }
+        else if (kind != 0) {
+            Fq dinv = inv * Fq::load(scratch + 32ull * (((size_t)warp * AFF_B + j) * 32u + lane));
+            inv = inv * d;
+            Fq num;
+            if (kind == 1) num = p2.y - p1.y;
+            else { Fq xx = p1.x.sqr(); num = xx.dbl() + xx; p2.x = p1.x; }
+            Fq lam = num * dinv;
+            r.x = lam.sqr() - p1.x - p2.x;
+            r.y = lam * (p1.x - r.x) - p1.y;
+        }
+        r.store(out_pts + 64ull * o);
+    }
+}
+
+// counts after the R regular rounds: cnt2[k] = padded slots of bucket k / 2^R  (cursor[k] - starts[k] = real count)
+__global__ void aff_counts_after_kernel(const uint32_t* __restrict__ starts, const uint32_t* __restrict__ cursor, uint32_t nb,
+                                        int R, uint32_t* __restrict__ cnt2) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nb) return;
+    const uint32_t pad = 1u << R, m = cursor[k] - starts[k];
+    cnt2[k] = ((m + pad - 1u) & ~(pad - 1u)) >> R;
+}
+
+// XYZZ task kernel over a compact point array (second stage of the batched-affine algorithm): same tasks, same
+// merge, but the entries are the points themselves.  starts[k] = first point of bucket k.
+__global__ void __launch_bounds__(128) msm_accumulate_pts_kernel(const uint8_t* __restrict__ pts, const uint32_t* __restrict__ starts,
+                                                                 const uint32_t* __restrict__ task_off, uint32_t n_buckets,
+                                                                 uint32_t total_pts, uint32_t task_len, bool top_down,
+                                                                 uint8_t* __restrict__ partial) {
+    const uint32_t n_tasks = task_off[n_buckets];
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_tasks) return;
+    const uint32_t t = top_down ? n_tasks - 1u - tid : tid;
+    uint32_t lo = 0, hi = n_buckets;
+    while (hi - lo > 1u) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (task_off[mid] <= t) lo = mid; else hi = mid;
+    }
+    const uint32_t k = lo;
+    uint32_t j = starts[k] + (t - task_off[k]) * task_len;
+    const uint32_t bucket_end = (k + 1 < n_buckets) ? starts[k + 1] : total_pts;
+    const uint32_t end = min(j + task_len, bucket_end);
+    XYZZ acc = XYZZ::identity();
+    for (; j < end; j++) {
+        Affine p = Affine::load(pts + 64ull * j);
+        if (!p.is_identity()) acc.add_affine(p, false);
+    }
+    acc.store(partial + 128ull * t);
+}
+
 // ---- segment reduction: segment `seg` of window `w` covers buckets [lo, lo+L) (0-based; bucket t
 // weighs t+1).  out = sum_t (t+1) * bucket[t] = (running-sum result) + lo * (plain sum).
 // Bucket k's value is partial[task_off[k]] (identity when the bucket has no task).
@@ -400,8 +548,8 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
     uint64_t task_len64 = std::max<uint64_t>(128, 2 * mean_load);
     if (nb < (1u << 17)) task_len64 = std::max<uint64_t>(32, std::min<uint64_t>(task_len64, ((uint64_t)n * W) >> 17));
     const uint32_t task_len = (uint32_t)task_len64;
-    const uint32_t max_multi = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / task_len + 1);
-    const uint32_t max_heavy = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / (32ull * task_len) + 1);
+    uint32_t max_multi = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / task_len + 1);
+    uint32_t max_heavy = (uint32_t)std::min<uint64_t>(nb, (uint64_t)n * W / (32ull * task_len) + 1);
     const uint32_t max_tasks = nb + (uint32_t)((uint64_t)n * W / task_len) + 1;
     cudaStream_t st = ctx->stream;
 
@@ -422,6 +570,19 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
     uint32_t* sorted = (uint32_t*)ctx->sorted.p;
     uint8_t* partial = (uint8_t*)ctx->buckets.p;
 
+    // batched-affine algorithm: R regular rounds over slices padded to 2^R slots, R from the mean bucket load
+    int R = 0;
+    if (ctx->msm_algo == 1) {
+        while (R < 5 && (mean_load >> (R + 3)) >= 1) R++;   // keep >= 8 real points per 2^R of padding
+    }
+    const uint32_t pad = 1u << R;
+    const uint64_t padded_ub = (uint64_t)n * W + (uint64_t)(pad - 1) * std::min<uint64_t>(nb, (uint64_t)n * W);
+    if (padded_ub + pad >= (1ull << 32)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: padded entry count overflows 32 bits");
+    // upper bound of the padded slot count, itself a multiple of 2^R; slots past the real total stay padding
+    const uint32_t total_padded = (uint32_t)((padded_ub + pad - 1) & ~(uint64_t)(pad - 1));
+    H2A_TRY(h2a_reserve(ctx, ctx->sorted, (size_t)total_padded * 4));
+    sorted = (uint32_t*)ctx->sorted.p;
+
     h2a_prof_begin(ctx, 0);
     H2A_CUDA(ctx, cudaMemsetAsync(offsets, 0, (size_t)nb * 4, st));
     H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 8, st));
@@ -429,20 +590,79 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
     msm_hist_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums);
+    scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, pad, block_sums);
     H2A_LAUNCH_CHECK(ctx);
     scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, scan_blocks);
     H2A_LAUNCH_CHECK(ctx);
-    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, block_sums, task_off, multi_list,
+    scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, pad, block_sums, task_off, multi_list,
                                                             max_multi + 1, n_multi);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
+    uint32_t* starts = nullptr;
+    if (R > 0) {   // keep the padded starts (the scatter turns `offsets` into cursors) and pre-fill the padding slots
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_u32, ((size_t)nb + 1) * 4 * 2 + 64));
+        starts = (uint32_t*)ctx->aff_u32.p;
+        H2A_CUDA(ctx, cudaMemcpyAsync(starts, offsets, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
+        H2A_CUDA(ctx, cudaMemsetAsync(sorted, 0xff, (size_t)total_padded * 4, st));
+    }
     msm_scatter_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, stride, first, offsets, sorted);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, !PRE,
+    if (R == 0) {
+        msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, !PRE,
                                                                        partial);
-    H2A_LAUNCH_CHECK(ctx);
+        H2A_LAUNCH_CHECK(ctx);
+    } else {
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_a, (size_t)(total_padded / 2) * 64));
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_b, (size_t)(total_padded / 4 + 1) * 64));
+        const uint64_t scratch_elems = (uint64_t)total_padded / 2 + 128ull * AFF_B;
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, scratch_elems * 32 + (scratch_elems / AFF_B + 4096) * 32));
+        uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p;
+        uint8_t* totals = scratch + scratch_elems * 32;
+        uint8_t* pts_in = nullptr;
+        uint8_t* pts_out = (uint8_t*)ctx->aff_a.p;
+        uint32_t n_out = total_padded / 2;
+        for (int round = 0; round < R; round++) {
+            const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
+            const uint32_t blocks = (threads + 127) / 128;
+            if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals);
+            else aff_forward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals);
+            H2A_LAUNCH_CHECK(ctx);
+            aff_invert_totals_kernel<<<(blocks * 128 / 64 + 63) / 64, 64, 0, st>>>(totals, blocks * 128);
+            H2A_LAUNCH_CHECK(ctx);
+            if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals, pts_out);
+            else aff_backward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals, pts_out);
+            H2A_LAUNCH_CHECK(ctx);
+            pts_in = pts_out;
+            pts_out = (pts_in == (uint8_t*)ctx->aff_a.p) ? (uint8_t*)ctx->aff_b.p : (uint8_t*)ctx->aff_a.p;
+            n_out /= 2;
+        }
+        // second stage: the surviving points (padded count / 2^R per bucket) through the XYZZ task machinery
+        const uint32_t total_pts = total_padded >> R;
+        uint32_t* starts2 = starts + (nb + 1);
+        aff_counts_after_kernel<<<(nb + 255) / 256, 256, 0, st>>>(starts, offsets, nb, R, starts2);
+        H2A_LAUNCH_CHECK(ctx);
+        const uint32_t task_len2 = std::max<uint32_t>(16, task_len >> R);
+        const uint32_t max_multi2 = (uint32_t)std::min<uint64_t>(nb, (uint64_t)total_pts / task_len2 + 1);
+        max_heavy = (uint32_t)std::min<uint64_t>(nb, (uint64_t)total_pts / (32ull * task_len2) + 1);
+        max_multi = max_multi2;
+        H2A_TRY(h2a_reserve(ctx, ctx->heavy, ((size_t)max_multi + 2) * 4));
+        multi_list = (uint32_t*)ctx->heavy.p;
+        H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 8, st));
+        scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(starts2, nb, task_len2, 1, block_sums);
+        H2A_LAUNCH_CHECK(ctx);
+        scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, scan_blocks);
+        H2A_LAUNCH_CHECK(ctx);
+        scan_apply_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(starts2, nb, task_len2, 1, block_sums, task_off, multi_list,
+                                                                max_multi + 1, n_multi);
+        H2A_LAUNCH_CHECK(ctx);
+        const uint32_t max_tasks2 = nb + total_pts / task_len2 + 1;
+        H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)max_tasks2 * 128));
+        partial = (uint8_t*)ctx->buckets.p;
+        msm_accumulate_pts_kernel<<<(max_tasks2 + 127) / 128, 128, 0, st>>>(pts_in, starts2, task_off, nb, total_pts, task_len2, !PRE,
+                                                                            partial);
+        H2A_LAUNCH_CHECK(ctx);
+    }
     msm_merge_heavy_kernel<<<(max_heavy + MERGE_WARPS - 1) / MERGE_WARPS, 32 * MERGE_WARPS, 0, st>>>(
         task_off, multi_list, max_multi + 1, n_multi, partial);
     H2A_LAUNCH_CHECK(ctx);

@@ -88,6 +88,9 @@ int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* s
 int h2a_g1_sum(const uint8_t* points_affine, size_t m, uint8_t out_affine[64]);
 /* Force the Pippenger window width (0 = automatic).  For tuning and tests. */
 int h2a_msm_set_window(h2a_ctx* ctx, int c);
+/* Bucket accumulation algorithm: 1 (default) pairwise tree of batched affine additions; 0 serial XYZZ mixed
+ * additions with one thread per bucket task.  Same result bit for bit; for A/B measurement and tests. */
+int h2a_msm_set_algorithm(h2a_ctx* ctx, int algo);
 
 /* ---- Fr NTT ------------------------------------------------------------------------------
  * Replaces halo2 `arithmetic::best_fft(a, omega, log_n)` and the `EvaluationDomain` methods

@@ -12,9 +12,11 @@ pytestmark = pytest.mark.gpu
 P, R = pm.P, pm.R
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=[1, 0], ids=["affine-tree", "xyzz-tasks"])
+def ctx(request):
+    """Every test runs with both bucket-accumulation algorithms of the MSM (h2a_msm_set_algorithm)."""
     c = h2a.Context(0)
+    c.set_msm_algorithm(request.param)
     yield c
     c.close()
 

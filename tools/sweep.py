@@ -20,10 +20,12 @@ def main():
     ap.add_argument("--ntt", default="16,18,20,22,24")
     ap.add_argument("--windows", default="")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--algo", type=int, default=1)
     ap.add_argument("--precompute", default="", help="comma list of table window widths to time as well")
     args = ap.parse_args()
     ctx = h2a.Context(0)
     ctx.set_profiling(True)
+    ctx.set_msm_algorithm(args.algo)
     stream = torch.cuda.ExternalStream(ctx.stream)
 
     def timeit(fn, reps):
