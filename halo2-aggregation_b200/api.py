@@ -222,6 +222,14 @@ class Context:
         self._check(self.lib.h2a_msm_g1_batch(self.h, bases.h, ptrs, ns, m, _ptr(out)))
         return out.reshape(m, 64)
 
+    def msm_batch_dev(self, bases, d_columns, ns):
+        m = len(d_columns)
+        ptrs = (ctypes.c_void_p * m)(*d_columns)
+        nn = (c_sz * m)(*ns)
+        out = np.zeros(64 * m, np.uint8)
+        self._check(self.lib.h2a_msm_g1_batch_dev(self.h, bases.h, ptrs, nn, m, _ptr(out)))
+        return out.reshape(m, 64)
+
     def msm_adhoc(self, bases_affine, scalars):
         b, s = _bytes(bases_affine), _bytes(scalars)
         if b.size // 64 != s.size // 32:
@@ -294,7 +302,7 @@ class Context:
         return out
 
     # ---- test hooks
-    FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "to_mont": 6, "from_mont": 7}
+    FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "sqr": 3, "inv": 4, "neg": 5, "to_mont": 6, "from_mont": 7, "inv_fast": 8}
 
     def field_op(self, field, op, a, b=None):
         a = _bytes(a)

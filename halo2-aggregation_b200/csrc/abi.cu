@@ -111,11 +111,59 @@ int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_
     return h2a_msm_run(ctx, bases, offset, (const uint8_t*)ctx->scalars.p, n, out_affine);
 }
 
+int h2a_msm_g1_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const void* const* d_scalars, const size_t* n, int m,
+                         uint8_t* out_affine) {
+    if (!ctx || !bases || !d_scalars || !n || !out_affine || m < 0) return H2A_ERR_INVALID;
+    for (int j = 0; j < m; j++)
+        if (n[j] > bases->n) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm batch: column %d has %zu scalars for %zu bases", j, n[j], bases->n);
+    return h2a_msm_batch_dev(ctx, bases, (const uint8_t* const*)d_scalars, n, m, out_affine);
+}
+
+// host scalars: column j is copied on its lane's stream while the other lane computes
 int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,
                      uint8_t* out_affine) {
     if (!ctx || !bases || !scalars || !n || !out_affine || m < 0) return H2A_ERR_INVALID;
-    for (int j = 0; j < m; j++) H2A_TRY(h2a_msm_g1(ctx, bases, 0, scalars[j], n[j], out_affine + 64 * j));
-    return H2A_OK;
+    for (int j = 0; j < m; j++)
+        if (n[j] > bases->n) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm batch: column %d has %zu scalars for %zu bases", j, n[j], bases->n);
+    if (m <= 1) {
+        for (int j = 0; j < m; j++) H2A_TRY(h2a_msm_g1(ctx, bases, 0, scalars[j], n[j], out_affine + 64 * j));
+        return H2A_OK;
+    }
+    h2a_ctx* alt = nullptr;
+    H2A_TRY(h2a_get_alt(ctx, &alt));
+    alt->msm_window_override = ctx->msm_window_override;
+    alt->msm_algo = ctx->msm_algo;
+    h2a_ctx* lanes[2] = {ctx, alt};
+    int pending_col[2] = {-1, -1};
+    const bool prof = ctx->profiling;
+    ctx->profiling = false;
+    int rc = H2A_OK;
+    for (int j = 0; j < m && rc == H2A_OK; j++) {
+        h2a_ctx* lane = lanes[j & 1];
+        if (pending_col[j & 1] >= 0) {
+            rc = h2a_msm_finish(lane, out_affine + 64 * pending_col[j & 1]);
+            pending_col[j & 1] = -1;
+            if (rc != H2A_OK) break;
+        }
+        rc = h2a_reserve(lane, lane->scalars, n[j] * 32 + 32);
+        if (rc == H2A_OK && n[j]) {
+            cudaError_t e = cudaMemcpyAsync(lane->scalars.p, scalars[j], n[j] * 32, cudaMemcpyHostToDevice, lane->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = H2A_ERR_CUDA; }
+        }
+        if (rc == H2A_OK) rc = h2a_msm_launch(lane, bases, 0, (const uint8_t*)lane->scalars.p, n[j]);
+        if (rc == H2A_OK) pending_col[j & 1] = j;
+        else if (lane != ctx) ctx->err = lane->err;
+    }
+    for (int l = 0; l < 2; l++) {
+        if (pending_col[l] >= 0) {
+            int r2 = h2a_msm_finish(lanes[l], out_affine + 64 * pending_col[l]);
+            if (rc == H2A_OK) rc = r2;
+        }
+    }
+    ctx->profiling = prof;
+    ctx->launches += alt->launches;
+    alt->launches = 0;
+    return rc;
 }
 
 int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* scalars, size_t n, uint8_t out_affine[64]) {

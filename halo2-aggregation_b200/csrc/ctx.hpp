@@ -41,6 +41,15 @@ struct h2a_ctx {
     void* pinned = nullptr;  // small pinned staging area for results
     size_t pinned_cap = 0;
 
+    // an MSM whose kernels are queued but whose window sums have not been combined yet (h2a_msm_launch / _finish)
+    struct {
+        bool active = false;
+        bool pre = false;
+        int c = 0;
+        uint32_t groups = 0;
+    } msm_pending;
+    h2a_ctx* alt = nullptr;  // second lane (own stream + workspace) for pipelined batches; created on first use
+
     // NTT workspace
     DevBuf ntt_a, ntt_b;
     std::map<uint32_t, NttTables*> ntt_tables;  // keyed by log_n of the twiddle table
@@ -98,3 +107,10 @@ void h2a_prof_end(h2a_ctx* ctx);
 int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n,
                 uint8_t out_affine[64]);
 int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c);
+// the two halves of h2a_msm_run: queue every kernel and the copy of the window sums (no host synchronisation), then
+// wait and combine on the host.  One MSM may be pending per ctx (lane).
+int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n);
+int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]);
+// m MSMs over the same bases with device-resident scalars, pipelined over two lanes
+int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m, uint8_t* out_affine);
+int h2a_get_alt(h2a_ctx* ctx, h2a_ctx** out);

@@ -137,6 +137,7 @@ __global__ void field_op_kernel(int op, const uint8_t* a, const uint8_t* b, uint
         case 4: r = x.inv(); break;
         case 6: r = x.to_mont(); break;
         case 7: r = x.from_mont(); break;
+        case 8: r = x.inv_fast(); break;
         default: r = x.neg(); break;
     }
     r.store(out + 32 * i);
@@ -246,6 +247,10 @@ int h2a_init(h2a_ctx** out, int device) {
 
 int h2a_destroy(h2a_ctx* ctx) {
     if (!ctx) return H2A_ERR_INVALID;
+    if (ctx->alt) {
+        h2a_destroy(ctx->alt);
+        ctx->alt = nullptr;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->scalars, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->buckets, &ctx->segsums,
@@ -260,6 +265,19 @@ int h2a_destroy(h2a_ctx* ctx) {
     delete ctx;
     return H2A_OK;
 }
+
+}  // extern "C"
+
+int h2a_get_alt(h2a_ctx* ctx, h2a_ctx** out) {
+    if (!ctx->alt) {
+        int rc = h2a_init(&ctx->alt, ctx->device);
+        if (rc != H2A_OK) H2A_FAIL(ctx, rc, "could not create the second lane");
+    }
+    *out = ctx->alt;
+    return H2A_OK;
+}
+
+extern "C" {
 
 const char* h2a_last_error(const h2a_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 void* h2a_stream(h2a_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -338,7 +356,7 @@ static int run_elementwise(h2a_ctx* ctx, int kind, int field, int op, const uint
     return H2A_OK;
 }
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
-    if (field < 0 || field > 1 || op < 0 || op > 7) return H2A_ERR_INVALID;
+    if (field < 0 || field > 1 || op < 0 || op > 8) return H2A_ERR_INVALID;
     if (op <= 2 && !b) return H2A_ERR_INVALID;
     return run_elementwise(ctx, 0, field, op, a, op <= 2 ? b : nullptr, out, n, 32);
 }

@@ -363,26 +363,49 @@ __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restr
     uint32_t o = base_o + lane;
 #pragma unroll 1
     for (int j = 0; j < AFF_B && o < n_out; j++, o += 32u) {
-        Affine p1 = load_input<FIRST>(bases, sorted, in_pts, 2u * o), p2 = load_input<FIRST>(bases, sorted, in_pts, 2u * o + 1u);
+        // the denominator of a generic addition needs the two x coordinates only: fetch the y halves just for the
+        // rare cases (an identity / padding slot, equal x) that pair_case has to tell apart
         Fq d;
-        pair_case(p1, p2, d);
+        const uint8_t *a1, *a2;
+        bool pad_slot = false;
+        if (FIRST) {
+            const uint32_t e1 = sorted[2u * o], e2 = sorted[2u * o + 1u];
+            pad_slot = e1 == 0xffffffffu || e2 == 0xffffffffu;
+            a1 = bases + 64ull * (e1 & 0x7fffffffu);
+            a2 = bases + 64ull * (e2 & 0x7fffffffu);
+        } else {
+            a1 = in_pts + 128ull * o;
+            a2 = a1 + 64;
+        }
+        bool slow = pad_slot;
+        if (!slow) {
+            Fq x1 = Fq::load(a1), x2 = Fq::load(a2);
+            d = x2 - x1;
+            slow = x1.is_zero() || x2.is_zero() || d.is_zero();
+        }
+        if (slow) {
+            Affine p1 = load_input<FIRST>(bases, sorted, in_pts, 2u * o), p2 = load_input<FIRST>(bases, sorted, in_pts, 2u * o + 1u);
+            pair_case(p1, p2, d);
+        }
         run.store(scratch + 32ull * (((size_t)warp * AFF_B + j) * 32u + lane));
         run = run * d;
     }
     run.store(totals + 32ull * t);
 }
-// in-place inversion of the chunk totals, 64 per thread with one field inversion (second level of Montgomery's trick)
+// in-place inversion of the chunk totals, INV_T per thread with one field inversion (second level of Montgomery's
+// trick).  The kernel is a pure latency chain, hence the short batch and the binary-Euclid inversion.
+constexpr uint32_t INV_T = 16;
 __global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restrict__ totals, uint32_t count) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lo = t * 64u;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lo = t * INV_T;
     if (lo >= count) return;
-    const uint32_t cnt = min(64u, count - lo);
-    Fq pre[64];
+    const uint32_t cnt = min(INV_T, count - lo);
+    Fq pre[INV_T];
     Fq run = Fq::one();
     for (uint32_t q = 0; q < cnt; q++) {
         pre[q] = run;
         run = run * Fq::load(totals + 32ull * (lo + q));
     }
-    Fq inv = run.inv();
+    Fq inv = run.inv_fast();
     for (uint32_t q = cnt; q-- > 0;) {
         Fq v = Fq::load(totals + 32ull * (lo + q));
         (inv * pre[q]).store(totals + 32ull * (lo + q));
@@ -520,15 +543,13 @@ __global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8
 int pick_window(size_t n) {  // from the measured sweep (tools/sweep.py --windows ...), B200
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
-    if (lg >= 19) return 16;
-    if (lg >= 17) return 15;
-    if (lg >= 14) return 10;
+    if (lg >= 17) return 16;
+    if (lg >= 14) return 15;
     return std::max(6, std::min(10, lg - 4));
 }
 
 template <int C, bool PRE>
-int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t first, const uint8_t* d_scalars, size_t n,
-              uint8_t out_affine[64]) {
+int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t first, const uint8_t* d_scalars, size_t n) {
     constexpr int W = Win<C>::W;
     constexpr uint32_t B = Win<C>::B;
     constexpr int BW = PRE ? 1 : W;  // windows of buckets
@@ -628,7 +649,7 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
             if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals);
             else aff_forward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals);
             H2A_LAUNCH_CHECK(ctx);
-            aff_invert_totals_kernel<<<(blocks * 128 / 64 + 63) / 64, 64, 0, st>>>(totals, blocks * 128);
+            aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, st>>>(totals, blocks * 128);
             H2A_LAUNCH_CHECK(ctx);
             if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals, pts_out);
             else aff_backward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals, pts_out);
@@ -675,16 +696,54 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
     H2A_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->winsums.p, (size_t)groups * 128, cudaMemcpyDeviceToHost, st));
-    H2A_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->msm_pending.active = true;
+    ctx->msm_pending.pre = PRE;
+    ctx->msm_pending.c = C;
+    ctx->msm_pending.groups = groups;
+    return H2A_OK;
+}
 
+}  // namespace
+
+int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n) {
+    if (ctx->msm_pending.active) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: a launch is already pending on this lane");
+    if (n == 0) {
+        ctx->msm_pending.active = true;
+        ctx->msm_pending.groups = 0;
+        return H2A_OK;
+    }
+    if (n > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n);
+    const bool pre = bases->table != nullptr && (ctx->msm_window_override == 0 || ctx->msm_window_override == bases->table_c);
+    int c = pre ? bases->table_c : (ctx->msm_window_override ? ctx->msm_window_override : pick_window(n));
+    switch (c) {
+#define H2A_CASE(C)                                                                                              \
+    case C:                                                                                                      \
+        return pre ? msm_launch_c<C, true>(ctx, bases->table, (uint32_t)bases->n, (uint32_t)offset, d_scalars, n) \
+                   : msm_launch_c<C, false>(ctx, bases->d + 64 * offset, 0, 0, d_scalars, n);
+        H2A_CASE(6) H2A_CASE(7) H2A_CASE(8) H2A_CASE(9) H2A_CASE(10) H2A_CASE(11) H2A_CASE(12) H2A_CASE(13)
+        H2A_CASE(14) H2A_CASE(15) H2A_CASE(16) H2A_CASE(17) H2A_CASE(18) H2A_CASE(19) H2A_CASE(20)
+#undef H2A_CASE
+        default:
+            H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: window width %d not in 6..20", c);
+    }
+}
+
+int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]) {
+    if (!ctx->msm_pending.active) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: nothing pending on this lane");
+    ctx->msm_pending.active = false;
+    if (ctx->msm_pending.groups == 0) {
+        memset(out_affine, 0, 64);
+        return H2A_OK;
+    }
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     using namespace h2a_host;
     const uint8_t* ws = (const uint8_t*)ctx->pinned;
     PointX acc = px_identity();
-    if (PRE) {  // the tables already carry the 2^(c*w) factors: plain sum of the slices
-        for (uint32_t g = 0; g < groups; g++) acc = px_add(acc, px_load(ws + 128 * g));
-    } else {    // Horner over the window sums: acc = acc * 2^c + S_w, top window first
-        for (int w = W - 1; w >= 0; w--) {
-            for (int i = 0; i < C; i++) acc = px_dbl(acc);
+    if (ctx->msm_pending.pre) {  // the tables already carry the 2^(c*w) factors: plain sum of the slices
+        for (uint32_t g = 0; g < ctx->msm_pending.groups; g++) acc = px_add(acc, px_load(ws + 128 * g));
+    } else {                     // Horner over the window sums: acc = acc * 2^c + S_w, top window first
+        for (int w = (int)ctx->msm_pending.groups - 1; w >= 0; w--) {
+            for (int i = 0; i < ctx->msm_pending.c; i++) acc = px_dbl(acc);
             acc = px_add(acc, px_load(ws + 128 * w));
         }
     }
@@ -694,33 +753,59 @@ int msm_run_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t fi
     return H2A_OK;
 }
 
-}  // namespace
-
 int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n,
                 uint8_t out_affine[64]) {
-    if (n == 0) {
-        memset(out_affine, 0, 64);
-        return H2A_OK;
+    H2A_TRY(h2a_msm_launch(ctx, bases, offset, d_scalars, n));
+    return h2a_msm_finish(ctx, out_affine);
+}
+
+// Two lanes alternate: while lane A's latency-bound tail (bucket reduction, window sums, copy back) drains, lane B's
+// histogram / scatter / accumulation kernels already occupy the SMs.  Lane B first waits for everything queued on the
+// main stream, so scalars produced there by earlier kernels are complete.
+int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m,
+                      uint8_t* out_affine) {
+    if (m <= 0) return H2A_OK;
+    if (m == 1) return h2a_msm_run(ctx, bases, 0, d_scalars[0], n[0], out_affine);
+    h2a_ctx* alt = nullptr;
+    H2A_TRY(h2a_get_alt(ctx, &alt));
+    alt->msm_window_override = ctx->msm_window_override;
+    alt->msm_algo = ctx->msm_algo;
+    cudaEvent_t ready;
+    H2A_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    H2A_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, ready, 0));
+    h2a_ctx* lanes[2] = {ctx, alt};
+    int pending_col[2] = {-1, -1};
+    int rc = H2A_OK;
+    const bool prof = ctx->profiling;
+    ctx->profiling = false;  // per-phase events of interleaved launches would be meaningless
+    for (int j = 0; j < m && rc == H2A_OK; j++) {
+        h2a_ctx* lane = lanes[j & 1];
+        if (pending_col[j & 1] >= 0) {
+            rc = h2a_msm_finish(lane, out_affine + 64 * pending_col[j & 1]);
+            pending_col[j & 1] = -1;
+            if (rc != H2A_OK) break;
+        }
+        rc = h2a_msm_launch(lane, bases, 0, d_scalars[j], n[j]);
+        if (rc == H2A_OK) pending_col[j & 1] = j;
+        else if (lane != ctx) ctx->err = lane->err;
     }
-    if (n > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n);
-    const bool pre = bases->table != nullptr && (ctx->msm_window_override == 0 || ctx->msm_window_override == bases->table_c);
-    int c = pre ? bases->table_c : (ctx->msm_window_override ? ctx->msm_window_override : pick_window(n));
-    switch (c) {
-#define H2A_CASE(C)                                                                                                     \
-    case C:                                                                                                             \
-        return pre ? msm_run_c<C, true>(ctx, bases->table, (uint32_t)bases->n, (uint32_t)offset, d_scalars, n, out_affine) \
-                   : msm_run_c<C, false>(ctx, bases->d + 64 * offset, 0, 0, d_scalars, n, out_affine);
-        H2A_CASE(6) H2A_CASE(7) H2A_CASE(8) H2A_CASE(9) H2A_CASE(10) H2A_CASE(11) H2A_CASE(12) H2A_CASE(13)
-        H2A_CASE(14) H2A_CASE(15) H2A_CASE(16) H2A_CASE(17) H2A_CASE(18) H2A_CASE(19) H2A_CASE(20)
-#undef H2A_CASE
-        default:
-            H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: window width %d not in 6..20", c);
+    for (int l = 0; l < 2; l++) {
+        if (pending_col[l] >= 0) {
+            int r2 = h2a_msm_finish(lanes[l], out_affine + 64 * pending_col[l]);
+            if (rc == H2A_OK) rc = r2;
+        }
     }
+    ctx->profiling = prof;
+    ctx->launches += alt->launches;
+    alt->launches = 0;
+    cudaEventDestroy(ready);
+    return rc;
 }
 
 // Builds T[w][i] = 2^(c*w) * P_i for w < ceil(254/c) next to the bases (W * n * 64 bytes of HBM).
 int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c) {
-    if (c < 0) c = bases->n >= (1u << 21) ? 20 : 16;  // automatic choice from the measured sweep
+    if (c < 0) c = bases->n >= (1u << 16) ? 20 : 16;  // automatic choice from the measured sweep
     if (c < 11 || c > 20) H2A_FAIL(ctx, H2A_ERR_INVALID, "precompute: window width %d not in 11..20", c);
     const int W = (254 + c - 1) / c;
     if ((uint64_t)bases->n * W >= (1ull << 31)) H2A_FAIL(ctx, H2A_ERR_INVALID, "precompute: %zu bases x %d windows too large", bases->n, W);

@@ -628,6 +628,16 @@ int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint3
     return H2A_OK;
 }
 
+// commitments of several device-resident columns over the same bases, pipelined over the two MSM lanes
+int commit_batch(h2a_ctx* ctx, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n, std::vector<hh::PointA>& out) {
+    std::vector<size_t> ns(cols.size(), n);
+    std::vector<uint8_t> pts(64 * cols.size());
+    H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data()));
+    out.resize(cols.size());
+    for (size_t i = 0; i < cols.size(); i++) out[i] = hh::affine_load(pts.data() + 64 * i);
+    return H2A_OK;
+}
+
 // inclusive prefix product of a[0..n) in place (tiles, then recursion over the tile totals)
 int scan_mul(h2a_ctx* ctx, uint8_t* a, uint32_t n, uint8_t* totals) {
     const uint32_t tiles = (n + dev::SCAN_TILE - 1) / dev::SCAN_TILE;
@@ -917,18 +927,23 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     enum { S_THETA = 0, S_BETA, S_GAMMA, S_Y, S_V, S_INIT, S_Z0, S_EVAL0 = 16 };
 
     tr.common_scalar(hh::fr_load(c->vk_hash));                                     // src/verifier.rs:341-358
-    for (uint32_t i = 0; i < s.n_instance; i++) {                                  // :360-363
-        H2A_CUDA(ctx, cudaMemcpyAsync(p->instance[i].lag, instance_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g_lagrange, p->instance[i].lag, n, cm));
-        if (!tr.common_point(cm)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
-        if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cm);
-    }
-    for (uint32_t i = 0; i < s.n_advice; i++) {                                    // :365-376
-        H2A_CUDA(ctx, cudaMemcpyAsync(p->advice[i].lag, advice_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g_lagrange, p->advice[i].lag, n, cm));
-        write_point(cm);
+    {   // instance (:360-363) and advice (:365-376) commitments in one pipelined batch
+        std::vector<const uint8_t*> cols;
+        for (uint32_t i = 0; i < s.n_instance; i++) {
+            H2A_CUDA(ctx, cudaMemcpyAsync(p->instance[i].lag, instance_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+            cols.push_back(p->instance[i].lag);
+        }
+        for (uint32_t i = 0; i < s.n_advice; i++) {
+            H2A_CUDA(ctx, cudaMemcpyAsync(p->advice[i].lag, advice_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+            cols.push_back(p->advice[i].lag);
+        }
+        std::vector<hh::PointA> cms;
+        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        for (uint32_t i = 0; i < s.n_instance; i++) {
+            if (!tr.common_point(cms[i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
+            if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cms[i]);
+        }
+        for (uint32_t i = 0; i < s.n_advice; i++) write_point(cms[s.n_instance + i]);
     }
     steps.mark("instance+advice commitments");
     hh::Fr theta = tr.squeeze();                                                   // :378
@@ -964,11 +979,13 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         H2A_CUDA(ctx, cudaMemcpyAsync(l.ps.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
         bl += 32ull * (n - u);
         bl += 32ull * bf;  // this lookup's Z tail, consumed after beta and gamma
-        hh::PointA ca, cs;
-        H2A_TRY(commit(ctx, p->g_lagrange, l.pa.lag, n, ca));
-        H2A_TRY(commit(ctx, p->g_lagrange, l.ps.lag, n, cs));
-        write_point(ca);
-        write_point(cs);
+    }
+    if (!s.lookups.empty()) {
+        std::vector<const uint8_t*> cols;
+        for (auto& l : p->lk) { cols.push_back(l.pa.lag); cols.push_back(l.ps.lag); }
+        std::vector<hh::PointA> cms;
+        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        for (auto& cm : cms) write_point(cm);
     }
     steps.mark("lookup permuted columns");
     hh::Fr beta = tr.squeeze(), gamma = tr.squeeze();                              // :390,393
@@ -1012,9 +1029,6 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         H2A_CUDA(ctx, cudaMemcpyAsync(slot(S_INIT), p->pz[ci].lag + 32ull * u, 32, cudaMemcpyDeviceToDevice, st));
         H2A_CUDA(ctx, cudaMemcpyAsync(p->pz[ci].lag + 32ull * (n - bf), bl, 32ull * bf, cudaMemcpyHostToDevice, st));
         bl += 32ull * bf;
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g_lagrange, p->pz[ci].lag, n, cm));
-        write_point(cm);
     }
     steps.mark("permutation grand products");
     for (size_t li = 0; li < s.lookups.size(); li++) {                             // :411-417, src/lookup.rs:81-106
@@ -1026,11 +1040,16 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         H2A_TRY(upload_fr(ctx, slot(S_Z0), hh::fr_one()));
         LAUNCH1D(dev::shift_scale_kernel, n, 256, p->tmp_n[2], slot(S_Z0), n, l.z.lag);
         H2A_CUDA(ctx, cudaMemcpyAsync(l.z.lag + 32ull * (n - bf), bl_lookup_z[li], 32ull * bf, cudaMemcpyHostToDevice, st));
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g_lagrange, l.z.lag, n, cm));
-        write_point(cm);
     }
-    steps.mark("lookup grand products");
+    {   // permutation Z (:402-409) then lookup Z (:411-417) commitments, one batch
+        std::vector<const uint8_t*> cols;
+        for (auto& q : p->pz) cols.push_back(q.lag);
+        for (auto& l : p->lk) cols.push_back(l.z.lag);
+        std::vector<hh::PointA> cms;
+        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        for (auto& cm : cms) write_point(cm);
+    }
+    steps.mark("lookup grand products + Z commitments");
     H2A_CUDA(ctx, cudaMemcpyAsync(p->random_coef, bl, 32ull * n, cudaMemcpyHostToDevice, st));   // src/vanishing.rs:54-75
     {
         hh::PointA cm;
@@ -1055,10 +1074,12 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         H2A_TRY(h2a_ntt_run(ctx, p->h_ext, m, p->h_ext, p->h_coef, s.ext_k, w, 1, p->coset));
     }
     steps.mark("quotient evaluation + extended_to_coeff");
-    for (uint32_t i = 0; i < s.qdeg; i++) {                                        // :427-434, src/vanishing.rs:77-106
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g, p->h_coef + 32ull * n * i, n, cm));
-        write_point(cm);
+    {                                                                              // :427-434, src/vanishing.rs:77-106
+        std::vector<const uint8_t*> cols;
+        for (uint32_t i = 0; i < s.qdeg; i++) cols.push_back(p->h_coef + 32ull * n * i);
+        std::vector<hh::PointA> cms;
+        H2A_TRY(commit_batch(ctx, p->g, cols, n, cms));
+        for (auto& cm : cms) write_point(cm);
     }
     steps.mark("h commitments");
     hh::Fr x = tr.squeeze();                                                       // :436
@@ -1124,19 +1145,35 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     std::map<int32_t, std::vector<size_t>> sets;
     for (size_t i = 0; i < mq.size(); i++) sets[mq[i].rot].push_back(i);
     const uint32_t nchunks = (n + dev::HORNER_L - 1) / dev::HORNER_L;
-    for (auto& kv : sets) {                                                        // src/multiopen.rs:344-395 (prover mirror)
-        uint8_t* batch = p->tmp_n[1];
-        bool first = true;
-        for (size_t qi : kv.second) { LAUNCH1D(dev::axpy_kernel, n, 256, batch, mq[qi].coef, slot(S_V), n, first ? 1 : 0); first = false; }
-        if (!point_slot.count(kv.first)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: rotation without evaluation point");
-        const uint8_t* d_z = slot(point_slot[kv.first]);
-        LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, batch, n, d_z, p->chunks);
-        dev::kate_carry_kernel<<<1, 128, 0, st>>>(p->chunks, nchunks, d_z, p->carries);
-        H2A_LAUNCH_CHECK(ctx);
-        LAUNCH1D(dev::kate_quotient_kernel, nchunks, 128, batch, n, d_z, p->carries, p->tmp_n[2]);
-        hh::PointA cm;
-        H2A_TRY(commit(ctx, p->g, p->tmp_n[2], n, cm));
-        write_point(cm);                                                           // src/multiopen.rs:392
+    {                                                                              // src/multiopen.rs:344-395 (prover mirror)
+        std::vector<const uint8_t*> wcols;
+        std::vector<hh::PointA> cms;
+        const size_t slots = m / n;                                                // quotients parked in the (now free) h_ext
+        size_t used = 0;
+        for (auto& kv : sets) {
+            uint8_t* batch = p->tmp_n[1];
+            bool first = true;
+            for (size_t qi : kv.second) { LAUNCH1D(dev::axpy_kernel, n, 256, batch, mq[qi].coef, slot(S_V), n, first ? 1 : 0); first = false; }
+            if (!point_slot.count(kv.first)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: rotation without evaluation point");
+            const uint8_t* d_z = slot(point_slot[kv.first]);
+            if (used == slots) {                                                   // more rotation sets than slots: flush
+                std::vector<hh::PointA> part;
+                H2A_TRY(commit_batch(ctx, p->g, wcols, n, part));
+                cms.insert(cms.end(), part.begin(), part.end());
+                wcols.clear();
+                used = 0;
+            }
+            uint8_t* q = p->h_ext + 32ull * n * used++;
+            LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, batch, n, d_z, p->chunks);
+            dev::kate_carry_kernel<<<1, 128, 0, st>>>(p->chunks, nchunks, d_z, p->carries);
+            H2A_LAUNCH_CHECK(ctx);
+            LAUNCH1D(dev::kate_quotient_kernel, nchunks, 128, batch, n, d_z, p->carries, q);
+            wcols.push_back(q);
+        }
+        std::vector<hh::PointA> part;
+        H2A_TRY(commit_batch(ctx, p->g, wcols, n, part));
+        cms.insert(cms.end(), part.begin(), part.end());
+        for (auto& cm : cms) write_point(cm);                                      // src/multiopen.rs:392
     }
     steps.mark("multiopen witnesses");
     *proof_len = pos;

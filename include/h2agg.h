@@ -81,6 +81,10 @@ int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const vo
 /* m scalar vectors (columns) over the same bases: out_affine[j] = MSM(scalars[j][0..n[j]), bases[0..n[j])) */
 int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,
                      uint8_t* out_affine /* m*64 */);
+/* Same with device-resident scalars.  Both batch calls pipeline the columns over two CUDA streams (lanes): the
+ * latency-bound tail of one MSM overlaps the bucket accumulation of the next. */
+int h2a_msm_g1_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const void* const* d_scalars, const size_t* n, int m,
+                         uint8_t* out_affine /* m*64 */);
 /* One-shot MSM over caller-supplied host bases (verifier-side sums; Params not involved). */
 int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* scalars, size_t n,
                      uint8_t out_affine[64]);
@@ -215,7 +219,7 @@ int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void*
 
 /* ---- test / measurement hooks ---------------------------------------------------------- */
 /* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inv 5 neg
- * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer. */
+ * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer, 8 inverse by binary Euclid. */
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);

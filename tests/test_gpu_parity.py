@@ -44,6 +44,7 @@ def test_field_ops(ctx, orc, field, mod):
     for op in ("add", "sub", "mul", "sqr", "neg"):
         assert bytes(ctx.field_op(field, op, am, bm)) == bytes(orc.field_op(field, op, am, bm)), op
     assert bytes(ctx.field_op(field, "inv", am[:32 * 64])) == bytes(orc.field_op(field, "inv", am[:32 * 64]))
+    assert bytes(ctx.field_op(field, "inv_fast", am[:32 * 2000])) == bytes(orc.field_op(field, "inv", am[:32 * 2000]))
     # all pairs of edge values through mul
     e = edge(mod)
     aa = orc.to_mont(field, ints_to_bytes([x for x in e for _ in e]))
@@ -235,6 +236,30 @@ def test_msm_batch_and_dev(ctx, orc):
     ctx.h2d(d, cols[0])
     assert bytes(ctx.msm_dev(hb, d, n)) == bytes(got[0])
     ctx.dev_free(d); hb.free()
+
+
+def test_msm_pipelined_batches(ctx, orc):
+    """h2a_msm_g1_batch / _batch_dev alternate columns over two lanes: same results as one call per column."""
+    n = 1 << 15
+    bases = orc.gen_bases(71, n)
+    hb = ctx.upload_bases(bases)
+    cols = [orc.gen_scalars(80 + j, n - 37 * j) for j in range(5)] + [np.zeros(0, np.uint8)]
+    want = [bytes(orc.msm(bases[:64 * (c.size // 32)], c)) if c.size else bytes(64) for c in cols]
+    got = ctx.msm_batch(hb, cols)
+    assert [bytes(g) for g in got] == want
+    hb.precompute(16)
+    got = ctx.msm_batch(hb, cols)
+    assert [bytes(g) for g in got] == want
+    dptrs = []
+    for c in cols[:5]:
+        d = ctx.dev_alloc(max(c.size, 32)); ctx.h2d(d, c); dptrs.append(d)
+    got = ctx.msm_batch_dev(hb, dptrs, [c.size // 32 for c in cols[:5]])
+    assert [bytes(g) for g in got] == want[:5]
+    # a single call after a batch still works (no pending state left behind)
+    assert bytes(ctx.msm(hb, cols[0])) == want[0]
+    for d in dptrs:
+        ctx.dev_free(d)
+    hb.free()
 
 
 def test_msm_linearity_at_bench_size(ctx):
