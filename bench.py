@@ -28,45 +28,52 @@ sys.path.insert(0, ROOT)
 METRIC = "G1 MSM Mpts/s at 2^22"
 UNIT = "Mpts/s"
 ALGO_BYTES_PER_POINT = 96          # 64 B affine base + 32 B scalar, each read once
-MODMUL_PER_MIXED_ADD = 10          # XYZZ madd-2008-s: 8M + 2S
-IMAD_PER_MODMUL = 136              # IMAD.WIDE per Montgomery product in our SASS (profiles/)
+MODMUL_PER_ADD = 6                 # batched affine addition: 3 (Montgomery's trick) + 2M + 1S
+ACCUMULATE_DRAM_BYTES = None       # dram bytes of the accumulation kernels per MSM, from profiles/ (ncu --set full)
 
 
 def clocks_monitor_start(dev_index):
-    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+    q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     try:
-        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+        return subprocess.Popen(["nvidia-smi", "-i", str(dev_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except OSError:
         return None
 
 
-def clocks_monitor_stop(proc):
+def clocks_monitor_stop(proc, t_begin, t_end):
+    """Samples whose timestamp falls inside the timed region [t_begin, t_end] (epoch seconds); when the region is
+    too short to hold one, the samples taken under load since the monitor started (warm-up + timed region)."""
     if proc is None:
         return None
+    import datetime
     proc.terminate()
     try:
         out, _ = proc.communicate(timeout=5)
     except subprocess.TimeoutExpired:
         proc.kill()
         out, _ = proc.communicate()
-    sm, mx, reasons = [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    rows = []
     for line in out.strip().splitlines():
         f = [x.strip() for x in line.split(",")]
-        if len(f) < 8:
+        if len(f) < 9:
             continue
         try:
-            sm.append(float(f[0])); mx.append(float(f[1]))
+            ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
         except ValueError:
             continue
-        for name, val in zip(names, f[4:8]):
-            if val.lower().startswith("active"):
-                reasons.add(name)
-    if not sm:
+    if not rows:
         return None
-    return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+    inside = [r for r in rows if t_begin <= r[0] <= t_end]
+    window = "timed region"
+    if not inside:
+        inside, window = rows, "warm-up + timed region (timed region shorter than the sampling period)"
+    reasons = sorted({x for r in inside for x in r[3]})
+    return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside), "samples": len(inside),
+            "window": window, "reasons": reasons}
 
 
 def cpu_msm_baseline(orc, target_seconds=15.0):
@@ -117,13 +124,15 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=22)
     ap.add_argument("--ref-log-n", type=int, default=20, help="points per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="plain Pippenger without the per-Params window tables")
+    ap.add_argument("--no-prove", action="store_true", help="skip the k=20 prover pipeline measurement (the metric's first half)")
+    ap.add_argument("--prove-k", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -198,11 +207,13 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), ctx.launch_count() - l0, phases, out
 
+    mon = clocks_monitor_start(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         r_dev = step_dev()
-    mon = clocks_monitor_start(local_rank) if rank == 0 else None
+    t_begin = time.time()
     ms_total, wall_ms, launches, phases, result = timed(step_dev, args.steps)
-    clocks = clocks_monitor_stop(mon)
+    t_end = time.time()
+    clocks = clocks_monitor_stop(mon, t_begin, t_end)
     for _ in range(2):
         step_e2e()
     e2e_ms, e2e_wall, _, _, r_e2e = timed(step_e2e, args.steps)
@@ -226,15 +237,21 @@ def main():
         avg = {nm: sum(ph[i][1] for ph in phases) / len(phases) for i, nm in enumerate(names)}
         acc_ms = avg.get("accumulate+merge", 0.0)
         imad_peak = ctx.bench_imad()
-        modmul_rate = ctx.bench_modmul()
+        modmul_peak = ctx.bench_modmul()
         if args.no_precompute:
-            c = 16 if args.log_n >= 19 else 15
+            c = 16 if args.log_n >= 17 else 15
         else:
-            c = 20 if args.log_n >= 21 else 16
+            c = 20 if args.log_n >= 16 else 16
         windows = (254 + c - 1) // c
         adds = n * windows
         achieved_gbs = ALGO_BYTES_PER_POINT * n / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
-        tera_imad = adds * MODMUL_PER_MIXED_ADD * IMAD_PER_MODMUL / (acc_ms * 1e-3) / 1e12 if acc_ms else 0.0
+        giga_mul = adds * MODMUL_PER_ADD / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "accumulate_dram_bytes.json")) as f:
+                traffic = json.load(f).get("bytes_per_msm_2^%d" % args.log_n)
+        except (OSError, ValueError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -245,21 +262,35 @@ def main():
                        "l2": "inputs %.0f MB per step exceed the 126 MB L2" % (ALGO_BYTES_PER_POINT * n / 1e6),
                        "e2e_bases": "resident in HBM (uploaded once, like Params); scalars come from pinned host memory every step"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * windows,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * 64,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / args.steps,
             "phases_ms": avg,
-            "roofline": {"kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak if hbm_peak else None, "traffic": None, "peak_source": peak_src,
+            "roofline": {"kernel": "bucket accumulation: aff_forward_kernel / aff_invert_totals_kernel / aff_backward_kernel rounds + msm_accumulate_pts_kernel",
+                         "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_source": peak_src,
                          "launch_ms": acc_ms,
-                         "note": "bucket accumulation is integer-pipe bound (254-bit Montgomery on 32-bit IMAD), see int_pipe"},
-            "int_pipe": {"kernel": "msm_accumulate_kernel", "achieved": tera_imad, "peak": imad_peak, "unit": "1e12 IMAD thread-instr/s",
-                         "frac": tera_imad / imad_peak if imad_peak else None,
-                         "peak_source": "h2a_bench_imad micro-benchmark, same run",
-                         "modmul_giga_per_s": modmul_rate,
-                         "algorithmic": "%d mixed adds x %d modmul x %d IMAD.WIDE" % (adds, MODMUL_PER_MIXED_ADD, IMAD_PER_MODMUL)},
+                         "note": "algorithmic 96 B/point over the duration of the accumulation kernels; the phase is bound by the "
+                                 "integer pipe (254-bit Montgomery products on IMAD.WIDE), see int_pipe"},
+            "int_pipe": {"kernel": "bucket accumulation", "achieved": giga_mul, "peak": modmul_peak, "unit": "1e9 Montgomery products/s",
+                         "frac": giga_mul / modmul_peak if modmul_peak else None,
+                         "peak_source": "h2a_bench_modmul micro-benchmark, same run (IMAD.WIDE-bound; 32-bit IMAD peak %.1f T/s)" % imad_peak,
+                         "algorithmic": "%d additions x %d products (batched affine)" % (adds, MODMUL_PER_ADD)},
         }
+        if world == 1 and not args.no_prove:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import prove_bench
+
+            class _A:
+                k, steps, lookups, precompute = args.prove_k, 2, 9, -1
+            bases.free()
+            del d_bases, d_scal
+            torch.cuda.empty_cache()
+            pr = prove_bench.run(ctx, _A)
+            line["prove"] = {"metric": pr["metric"], "value": pr["value"], "unit": "s", "higher_is_better": False,
+                             "proof_verifies": pr["proof_verifies"], "phases_ms": pr["phases_ms"], "workload": pr["config"]["workload"]}
+            bases = None
         if not args.no_cpu_baseline and world == 1:
             from oracle import loader as orc
             line["cpu_baseline"], _ = cpu_msm_baseline(orc)
@@ -269,7 +300,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    bases.free()
+    if bases is not None:
+        bases.free()
     ctx.close()
 
 

@@ -23,9 +23,12 @@ struct h2a_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;       // second stream of this lane (the two halves of the affine tree)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
+    int msm_seg_len = 32;  // buckets per thread in the segmented bucket reduction
     int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
     // profiling

@@ -239,6 +239,8 @@ int h2a_init(h2a_ctx** out, int device) {
     }
     const char* env = getenv("H2A_MSM_WINDOW");
     if (env) ctx->msm_window_override = atoi(env);
+    env = getenv("H2A_MSM_SEG");
+    if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_seg_len = atoi(env);
     env = getenv("H2A_MSM_ALGO");
     if (env) ctx->msm_algo = atoi(env) ? 1 : 0;
     *out = ctx;
@@ -261,6 +263,9 @@ int h2a_destroy(h2a_ctx* ctx) {
     h2a_ntt_free_tables(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return H2A_OK;

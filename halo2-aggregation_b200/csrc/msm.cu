@@ -556,7 +556,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     const uint32_t nb = (uint32_t)BW * B;
     if ((uint64_t)n * W >= (1ull << 32) || (PRE && (uint64_t)stride * W >= (1ull << 31)))
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
-    const uint32_t seg_len = std::max(1u, std::min(32u, B / 32u));
+    const uint32_t seg_len = std::max(1u, std::min((uint32_t)ctx->msm_seg_len, B / 32u));
     const uint32_t segs = B / seg_len;
     // groups of segment sums returned to the host: one per window, or (PRE) 64 slices of the single window
     const uint32_t groups = PRE ? std::min(64u, segs) : (uint32_t)W;
@@ -598,9 +598,9 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     }
     const uint32_t pad = 1u << R;
     const uint64_t padded_ub = (uint64_t)n * W + (uint64_t)(pad - 1) * std::min<uint64_t>(nb, (uint64_t)n * W);
-    if (padded_ub + pad >= (1ull << 32)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: padded entry count overflows 32 bits");
+    if (padded_ub + 2ull * pad >= (1ull << 32)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: padded entry count overflows 32 bits");
     // upper bound of the padded slot count, itself a multiple of 2^R; slots past the real total stay padding
-    const uint32_t total_padded = (uint32_t)((padded_ub + pad - 1) & ~(uint64_t)(pad - 1));
+    const uint32_t total_padded = (uint32_t)((padded_ub + 2ull * pad - 1) & ~(uint64_t)(2ull * pad - 1));   // two equal halves per round
     H2A_TRY(h2a_reserve(ctx, ctx->sorted, (size_t)total_padded * 4));
     sorted = (uint32_t*)ctx->sorted.p;
 
@@ -636,28 +636,48 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     } else {
         H2A_TRY(h2a_reserve(ctx, ctx->aff_a, (size_t)(total_padded / 2) * 64));
         H2A_TRY(h2a_reserve(ctx, ctx->aff_b, (size_t)(total_padded / 4 + 1) * 64));
-        const uint64_t scratch_elems = (uint64_t)total_padded / 2 + 128ull * AFF_B;
-        H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, scratch_elems * 32 + (scratch_elems / AFF_B + 4096) * 32));
-        uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p;
-        uint8_t* totals = scratch + scratch_elems * 32;
-        uint8_t* pts_in = nullptr;
-        uint8_t* pts_out = (uint8_t*)ctx->aff_a.p;
-        uint32_t n_out = total_padded / 2;
-        for (int round = 0; round < R; round++) {
-            const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
-            const uint32_t blocks = (threads + 127) / 128;
-            if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals);
-            else aff_forward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals);
-            H2A_LAUNCH_CHECK(ctx);
-            aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, st>>>(totals, blocks * 128);
-            H2A_LAUNCH_CHECK(ctx);
-            if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, st>>>(d_bases, sorted, nullptr, n_out, scratch, totals, pts_out);
-            else aff_backward_kernel<false><<<blocks, 128, 0, st>>>(nullptr, nullptr, pts_in, n_out, scratch, totals, pts_out);
-            H2A_LAUNCH_CHECK(ctx);
-            pts_in = pts_out;
-            pts_out = (pts_in == (uint8_t*)ctx->aff_a.p) ? (uint8_t*)ctx->aff_b.p : (uint8_t*)ctx->aff_a.p;
-            n_out /= 2;
+        // the two halves of the slot array are independent trees: they run on two streams so that one half's
+        // forward / backward kernels fill the latency gap of the other half's totals inversion
+        if (!ctx->stream2) H2A_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        if (!ctx->ev_fork) {
+            H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         }
+        const uint32_t half_out0 = total_padded / 4;                                // outputs of round 0 per half
+        const uint64_t scratch_elems = (uint64_t)half_out0 + 128ull * AFF_B;       // per half
+        const uint64_t totals_elems = scratch_elems / AFF_B + 4096;
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, 2 * (scratch_elems + totals_elems) * 32));
+        H2A_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        H2A_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        uint8_t* pts_final = nullptr;
+        for (int half = 0; half < 2; half++) {
+            cudaStream_t hs = half ? ctx->stream2 : st;
+            uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p + (size_t)half * (scratch_elems + totals_elems) * 32;
+            uint8_t* totals = scratch + scratch_elems * 32;
+            uint8_t* pts_in = nullptr;
+            uint8_t* pts_out = (uint8_t*)ctx->aff_a.p;
+            uint32_t n_out = half_out0;
+            for (int round = 0; round < R; round++) {
+                const size_t o0 = (size_t)half * n_out;                            // first output of this half in this round
+                const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
+                const uint32_t blocks = (threads + 127) / 128;
+                if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals);
+                else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, scratch, totals);
+                H2A_LAUNCH_CHECK(ctx);
+                aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, hs>>>(totals, blocks * 128);
+                H2A_LAUNCH_CHECK(ctx);
+                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals, pts_out + 64 * o0);
+                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, scratch, totals, pts_out + 64 * o0);
+                H2A_LAUNCH_CHECK(ctx);
+                pts_in = pts_out;
+                pts_out = (pts_in == (uint8_t*)ctx->aff_a.p) ? (uint8_t*)ctx->aff_b.p : (uint8_t*)ctx->aff_a.p;
+                n_out /= 2;
+            }
+            pts_final = pts_in;
+        }
+        H2A_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+        H2A_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        uint8_t* pts_in = pts_final;
         // second stage: the surviving points (padded count / 2^R per bucket) through the XYZZ task machinery
         const uint32_t total_pts = total_padded >> R;
         uint32_t* starts2 = starts + (nb + 1);

@@ -113,14 +113,7 @@ def random_blinds(ctx, count, seed):
     return raw.reshape(-1)                             # any value < 2^252 is a valid Montgomery-form element
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--k", type=int, default=20)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--lookups", type=int, default=9)
-    ap.add_argument("--precompute", type=int, default=-1, help="window bits of the per-Params MSM tables (0 = none)")
-    args = ap.parse_args()
-    ctx = h2a.Context(0)
+def run(ctx, args):
     secret = 0x0f1e2d3c4b5a69788796a5b4c3d2e1f00112233445566778899aabbccddeeff % R
     t0 = time.perf_counter()
     g, gl = ctx.kzg_setup(args.k, fr(ctx, [secret]))
@@ -147,14 +140,27 @@ def main():
     rhs = h2a.g1_sum(np.concatenate([zw, f, e]))
     ok = bytes(lhs) == bytes(rhs)
     best = min(times[1:])
-    print(json.dumps({"metric": "agg-circuit prove s at k=%d" % args.k, "value": best, "unit": "s", "higher_is_better": False,
+    circ.free(); g.free(); gl.free()
+    return ({"metric": "agg-circuit prove s at k=%d" % args.k, "value": best, "unit": "s", "higher_is_better": False,
                       "steps": args.steps, "all_s": times[1:], "first_call_s": times[0], "proof_bytes": len(proof), "proof_verifies": ok,
                       "config": {"workload": "prover pipeline, synthetic aggregation-circuit profile (SURVEY §7): 8 advice, %d fixed, %d lookups, "
                                              "9 permutation columns (3 chunks), degree 5, ext domain 2^%d; witness columns in host memory" %
                                              (shape.num_fixed, args.lookups, args.k + 2),
                                  "msm_tables": args.precompute},
-                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys}), flush=True)
-    if not ok:
+                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--lookups", type=int, default=9)
+    ap.add_argument("--precompute", type=int, default=-1, help="window bits of the per-Params MSM tables (0 = none)")
+    args = ap.parse_args()
+    ctx = h2a.Context(0)
+    res = run(ctx, args)
+    print(json.dumps(res), flush=True)
+    if not res["proof_verifies"]:
         sys.exit("proof does not satisfy the pairing relation")
 
 
