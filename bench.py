@@ -214,6 +214,12 @@ def main():
     ms_total, wall_ms, launches, phases, result = timed(step_dev, args.steps)
     t_end = time.time()
     clocks = clocks_monitor_stop(mon, t_begin, t_end)
+    # the same K MSMs issued through the pipelined batch entry point (two lanes), as the prover commits its columns
+    def batch_dev():
+        return ctx.msm_batch_dev(bases, [d_scal.data_ptr()] * args.steps, [n] * args.steps)
+    batch_dev()
+    bat_ms, _, _, _, r_bat = timed(batch_dev, 1)
+    assert all(bytes(combine(r)) == bytes(result) for r in r_bat), "batched and single results differ"
     for _ in range(2):
         step_e2e()
     e2e_ms, e2e_wall, _, _, r_e2e = timed(step_e2e, args.steps)
@@ -266,6 +272,8 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "wall_ms_per_step": wall_ms / args.steps,
+            "batched": {"value": total_pts / (bat_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": bat_ms / args.steps,
+                        "note": "the same %d MSMs through h2a_msm_g1_batch_dev (two pipelined lanes); not the headline value" % args.steps},
             "phases_ms": avg,
             "roofline": {"kernel": "bucket accumulation: aff_forward_kernel / aff_invert_totals_kernel / aff_backward_kernel rounds + msm_accumulate_pts_kernel",
                          "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

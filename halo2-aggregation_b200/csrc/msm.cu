@@ -647,8 +647,8 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
         const uint64_t scratch_elems = (uint64_t)half_out0 + 128ull * AFF_B;       // per half
         const uint64_t totals_elems = scratch_elems / AFF_B + 4096;
         H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, 2 * (scratch_elems + totals_elems) * 32));
-        H2A_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        H2A_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+        // the second stream starts one phase late (after the first half's round-0 forward pass): the halves then run
+        // out of step and each one's latency-bound inversion hides under the other's forward / backward kernel
         uint8_t* pts_final = nullptr;
         for (int half = 0; half < 2; half++) {
             cudaStream_t hs = half ? ctx->stream2 : st;
@@ -664,6 +664,10 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals);
                 else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, scratch, totals);
                 H2A_LAUNCH_CHECK(ctx);
+                if (half == 0 && round == 0) {
+                    H2A_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+                    H2A_CUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+                }
                 aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, hs>>>(totals, blocks * 128);
                 H2A_LAUNCH_CHECK(ctx);
                 if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals, pts_out + 64 * o0);
