@@ -22,5 +22,6 @@ from .api import (  # noqa: F401
     declared_symbols,
     g1_sum,
     fr_root_of_unity,
+    xorshift_scalar,
 )
 from .dist import allgather_points, allgather_sum, shard_range  # noqa: F401

@@ -88,6 +88,16 @@ def fr_root_of_unity(k):
     return out
 
 
+def xorshift_scalar(seed16):
+    """The KZG secret the reference's seeded XorShiftRng yields (examples/simple-example.rs:584-589)."""
+    seed = np.frombuffer(bytes(seed16), dtype=np.uint8)
+    out = np.zeros(32, np.uint8)
+    rc = load_library().h2a_xorshift_scalar(_ptr(seed), _ptr(out))
+    if rc != 0:
+        raise H2AError(rc, "xorshift_scalar")
+    return out
+
+
 def g1_sum(points):
     pts = _bytes(points)
     out = np.zeros(64, np.uint8)

@@ -166,6 +166,25 @@ using h2a_glue::expand_proof;
 
 extern "C" {
 
+// rand_xorshift 0.3 XorShiftRng::from_seed + 64 bytes of fill_bytes -> Fr::from_bytes_wide: the draw that
+// `Setup::<Bn256>::new(k, XorShiftRng::from_seed(seed))` makes for the KZG secret (examples/simple-example.rs:584-589).
+// The Fr::random convention is upstream-inferred; the stream itself is the published algorithm.
+int h2a_xorshift_scalar(const uint8_t seed[16], uint8_t out_scalar[32]) {
+    if (!seed || !out_scalar) return H2A_ERR_INVALID;
+    uint32_t st[4];
+    memcpy(st, seed, 16);
+    if ((st[0] | st[1] | st[2] | st[3]) == 0) st[0] = st[1] = st[2] = st[3] = 0x0BAD5EEDu;
+    uint8_t wide[64];
+    for (int i = 0; i < 16; i++) {
+        uint32_t t = st[0] ^ (st[0] << 11);
+        st[0] = st[1]; st[1] = st[2]; st[2] = st[3];
+        st[3] = st[3] ^ (st[3] >> 19) ^ (t ^ (t >> 8));
+        memcpy(wide + 4 * i, &st[3], 4);
+    }
+    h2a_host::fr_store(out_scalar, h2a_glue::fr_from_wide(wide));
+    return H2A_OK;
+}
+
 h2a_transcript* h2a_transcript_new(void) { return new h2a_transcript(); }
 void h2a_transcript_free(h2a_transcript* t) { delete t; }
 int h2a_transcript_common_point(h2a_transcript* t, const uint8_t point_affine[64]) {

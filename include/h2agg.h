@@ -196,6 +196,9 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* circuit, const uint8_t* instance
  * The Lagrange basis uses the closed form L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)) — fixed-base
  * multiplications only, no group FFT.  Returns two resident handles (free with h2a_bases_free). */
 int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s[32], h2a_bases** out_g, h2a_bases** out_g_lagrange);
+/* The scalar that `XorShiftRng::from_seed(seed)` yields for the KZG secret (examples/simple-example.rs:584-589):
+ * rand_xorshift 0.3 stream, 64 bytes, Fr::from_bytes_wide (the last step is upstream-inferred). Host only. */
+int h2a_xorshift_scalar(const uint8_t seed[16], uint8_t out_scalar[32]);
 /* Copy resident bases back to the host (n * 64 bytes), e.g. to write a params file. */
 int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy);
 /* Per-phase device times (ms) of the last h2a_create_proof; returns the number of phases written. */

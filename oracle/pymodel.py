@@ -230,3 +230,36 @@ def gwc_accumulate(queries, ws, x, u, v, omega, g1=G1):
         e_acc = (e_acc * u + eb) % R                                       # :406-409,467-469
     e = g1_mul(g1, (-e_acc) % R)                                           # :490-492
     return e, f_acc, w_acc, zw_acc
+
+
+# ---------------------------------------------------------------- setup randomness
+class XorShiftRng:
+    """rand_xorshift 0.3 `XorShiftRng::from_seed([u8; 16])` (Cargo.toml:16; seeded at
+    examples/simple-example.rs:584-587): four little-endian u32 words x, y, z, w; all-zero seeds are replaced."""
+
+    def __init__(self, seed16):
+        seed16 = bytes(seed16)
+        assert len(seed16) == 16
+        self.x, self.y, self.z, self.w = (int.from_bytes(seed16[4 * i:4 * i + 4], "little") for i in range(4))
+        if (self.x | self.y | self.z | self.w) == 0:
+            self.x, self.y, self.z, self.w = 0x0BAD5EED, 0x0BAD5EED, 0x0BAD5EED, 0x0BAD5EED
+
+    def next_u32(self):
+        t = (self.x ^ (self.x << 11)) & 0xFFFFFFFF
+        self.x, self.y, self.z = self.y, self.z, self.w
+        self.w = (self.w ^ (self.w >> 19) ^ (t ^ (t >> 8))) & 0xFFFFFFFF
+        return self.w
+
+    def fill_bytes(self, n):
+        out = bytearray()
+        while len(out) < n:
+            out += self.next_u32().to_bytes(4, "little")
+        return bytes(out[:n])
+
+
+REFERENCE_SETUP_SEED = bytes([0x59, 0x62, 0xbe, 0x5d, 0x76, 0x3d, 0x31, 0x8d, 0x17, 0xdb, 0x37, 0x32, 0x54, 0x06, 0xbc, 0xe5])
+
+
+def setup_secret_from_seed(seed16=REFERENCE_SETUP_SEED):
+    """[UPSTREAM-INFERRED] `Fr::random(rng)` of the dependency = from_bytes_wide over 64 bytes of the stream."""
+    return int.from_bytes(XorShiftRng(seed16).fill_bytes(64), "little") % R

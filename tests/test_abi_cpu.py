@@ -70,3 +70,28 @@ def test_g1_sum_matches_oracle(orc):
     dbl = np.frombuffer(pm.affine_bytes(p) * 2, dtype=np.uint8)
     assert pm.affine_from_bytes(h2a.g1_sum(dbl)) == pm.g1_mul(pm.G1, 10)
     assert bytes(h2a.g1_sum(np.zeros(0, np.uint8))) == bytes(64)
+
+
+def test_xorshift_setup_secret_matches_model():
+    """The reference seeds its KZG setup with a fixed XorShift seed (examples/simple-example.rs:584-587)."""
+    got = h2a.xorshift_scalar(pm.REFERENCE_SETUP_SEED)
+    assert pm.fr_from_mont_bytes(got) == pm.setup_secret_from_seed()
+    seed = bytes(range(1, 17))
+    rng = pm.XorShiftRng(seed)
+    first = rng.next_u32()
+    x, y, z, w = (int.from_bytes(seed[4 * i:4 * i + 4], "little") for i in range(4))
+    t = (x ^ (x << 11)) & 0xFFFFFFFF
+    assert first == (w ^ (w >> 19) ^ (t ^ (t >> 8))) & 0xFFFFFFFF
+    assert pm.fr_from_mont_bytes(h2a.xorshift_scalar(bytes(16))) == pm.setup_secret_from_seed(bytes(16))   # all-zero seed is replaced
+    assert h2a.load_library().h2a_xorshift_scalar(None, None) == -1
+
+
+def test_argument_errors_without_a_device():
+    import ctypes
+    lib = h2a.load_library()
+    out = np.zeros(64, np.uint8)
+    assert lib.h2a_g1_sum(None, ctypes.c_size_t(3), out.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert lib.h2a_transcript_common_point(None, None) == -1
+    assert lib.h2a_init(None, 0) == -1
+    assert lib.h2a_destroy(None) == -1
+    assert lib.h2a_blinds_len(None) == 0 and lib.h2a_proof_len(None) == 0
