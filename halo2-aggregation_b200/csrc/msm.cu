@@ -215,7 +215,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint32_t* __re
             else if (nt > 1u) multi_list[atomicAdd(n_multi, 1u)] = base + k;
         }
         ex += v[k];
-        if (base + k == n - 1) task_off[n] = (uint32_t)(ex >> 32);
+        if (base + k == n - 1) {
+            task_off[n] = (uint32_t)(ex >> 32);
+            n_multi[2] = (uint32_t)ex;   // total slots (padded): everything beyond it in the sorted array is padding
+        }
     }
 }
 
@@ -356,9 +359,14 @@ __device__ __forceinline__ Affine load_input(const uint8_t* __restrict__ bases, 
 template <bool FIRST>
 __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                           const uint8_t* __restrict__ in_pts, uint32_t n_out,
+                                                          const uint32_t* __restrict__ total_slots, uint32_t o0, int round,
                                                           uint8_t* __restrict__ scratch, uint8_t* __restrict__ totals) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t base_o = warp * 32u * AFF_B;
+    {   // outputs past the real slots of this round are padding only: clip (o0 = first output of this half)
+        const uint32_t live = (*total_slots + (2u << round) - 1u) >> (round + 1);
+        n_out = live > o0 ? min(n_out, live - o0) : 0u;
+    }
     Fq run = Fq::one();
     uint32_t o = base_o + lane;
 #pragma unroll 1
@@ -416,10 +424,15 @@ __global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restri
 template <bool FIRST>
 __global__ void __launch_bounds__(128) aff_backward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                            const uint8_t* __restrict__ in_pts, uint32_t n_out,
+                                                           const uint32_t* __restrict__ total_slots, uint32_t o0, int round,
                                                            const uint8_t* __restrict__ scratch, const uint8_t* __restrict__ totals,
                                                            uint8_t* __restrict__ out_pts) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, warp = t >> 5, lane = t & 31;
     const uint32_t base_o = warp * 32u * AFF_B;
+    {
+        const uint32_t live = (*total_slots + (2u << round) - 1u) >> (round + 1);
+        n_out = live > o0 ? min(n_out, live - o0) : 0u;
+    }
     if (base_o + lane >= n_out) return;
     const uint32_t cnt = min((uint32_t)AFF_B, (n_out - base_o - lane + 31u) / 32u);  // outputs of this lane
     Fq inv = Fq::load(totals + 32ull * t);
@@ -459,8 +472,8 @@ __global__ void aff_counts_after_kernel(const uint32_t* __restrict__ starts, con
 // merge, but the entries are the points themselves.  starts[k] = first point of bucket k.
 __global__ void __launch_bounds__(128) msm_accumulate_pts_kernel(const uint8_t* __restrict__ pts, const uint32_t* __restrict__ starts,
                                                                  const uint32_t* __restrict__ task_off, uint32_t n_buckets,
-                                                                 uint32_t total_pts, uint32_t task_len, bool top_down,
-                                                                 uint8_t* __restrict__ partial) {
+                                                                 const uint32_t* __restrict__ total_pts, uint32_t task_len,
+                                                                 bool top_down, uint8_t* __restrict__ partial) {
     const uint32_t n_tasks = task_off[n_buckets];
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n_tasks) return;
@@ -472,7 +485,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_pts_kernel(const uint8_t* 
     }
     const uint32_t k = lo;
     uint32_t j = starts[k] + (t - task_off[k]) * task_len;
-    const uint32_t bucket_end = (k + 1 < n_buckets) ? starts[k + 1] : total_pts;
+    const uint32_t bucket_end = (k + 1 < n_buckets) ? starts[k + 1] : *total_pts;   // real total, left by the scan
     const uint32_t end = min(j + task_len, bucket_end);
     XYZZ acc = XYZZ::identity();
     for (; j < end; j++) {
@@ -661,8 +674,8 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 const size_t o0 = (size_t)half * n_out;                            // first output of this half in this round
                 const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
                 const uint32_t blocks = (threads + 127) / 128;
-                if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals);
-                else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, scratch, totals);
+                if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
+                else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
                 H2A_LAUNCH_CHECK(ctx);
                 if (half == 0 && round == 0) {
                     H2A_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
@@ -670,8 +683,8 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 }
                 aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, hs>>>(totals, blocks * 128);
                 H2A_LAUNCH_CHECK(ctx);
-                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, scratch, totals, pts_out + 64 * o0);
-                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, scratch, totals, pts_out + 64 * o0);
+                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out + 64 * o0);
+                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out + 64 * o0);
                 H2A_LAUNCH_CHECK(ctx);
                 pts_in = pts_out;
                 pts_out = (pts_in == (uint8_t*)ctx->aff_a.p) ? (uint8_t*)ctx->aff_b.p : (uint8_t*)ctx->aff_a.p;
@@ -704,7 +717,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
         const uint32_t max_tasks2 = nb + total_pts / task_len2 + 1;
         H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)max_tasks2 * 128));
         partial = (uint8_t*)ctx->buckets.p;
-        msm_accumulate_pts_kernel<<<(max_tasks2 + 127) / 128, 128, 0, st>>>(pts_in, starts2, task_off, nb, total_pts, task_len2, !PRE,
+        msm_accumulate_pts_kernel<<<(max_tasks2 + 127) / 128, 128, 0, st>>>(pts_in, starts2, task_off, nb, n_multi + 2, task_len2, !PRE,
                                                                             partial);
         H2A_LAUNCH_CHECK(ctx);
     }

@@ -416,6 +416,48 @@ __global__ void __launch_bounds__(1024) bitonic_tail_kernel(uint8_t* keys, uint3
         g[1] = hi[t];
     }
 }
+// ---- counting sort for small keys (range tables and the like): every key < 2^COUNT_BITS fits one counter
+constexpr uint32_t COUNT_BITS = 20;
+// stats[0] |= OR of limbs 1..7 of all keys, stats[1] = max of limb 0   (decides which sort applies)
+__global__ void key_stats_kernel(const uint8_t* keys, uint32_t u, uint32_t* stats) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t hi = 0, lo = 0;
+    if (i < u) {
+        Fr k = ld(keys, i);
+        hi = k.l[1] | k.l[2] | k.l[3] | k.l[4] | k.l[5] | k.l[6] | k.l[7];
+        lo = k.l[0];
+    }
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    lo = __reduce_max_sync(0xffffffffu, lo);
+    if ((threadIdx.x & 31) == 0) {
+        if (hi) atomicOr(&stats[0], hi);
+        atomicMax(&stats[1], lo);
+    }
+}
+__global__ void count_keys_kernel(const uint8_t* keys, uint32_t u, uint32_t* hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < u) atomicAdd(&hist[ld(keys, i).l[0]], 1u);
+}
+// out[p] = the key whose run covers position p (offsets = exclusive prefix of the counters), sentinel beyond u
+__global__ void expand_counts_kernel(const uint32_t* offsets, uint32_t bins, uint32_t u, uint32_t n, uint8_t* out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    Fr k;
+    if (p < u) {
+        uint32_t lo = 0, hi = bins;  // largest v with offsets[v] <= p
+        while (hi - lo > 1u) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (offsets[mid] <= p) lo = mid; else hi = mid;
+        }
+        k = Fr::zero();
+        k.l[0] = lo;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) k.l[j] = 0xffffffffu;
+    }
+    k.store(out + 32ull * p);
+}
+
 // first[row] = 1 when row starts a run of equal inputs; used[j] = 1 for the table entry matched to that run
 __global__ void lookup_match_kernel(const uint8_t* ka, const uint8_t* ks, uint32_t u, uint32_t* rep, uint32_t* unused, uint32_t* err) {
     uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -556,6 +598,7 @@ struct ProverState {
     uint8_t *omega_pows = nullptr;                                        // omega^i, i < n
     uint8_t *chunks = nullptr, *carries = nullptr, *totals = nullptr, *small = nullptr;
     uint32_t* u32buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // rep, unused, rep_rank, unused_rank, tile sums / counters
+    uint32_t* count_buf = nullptr;                                        // counting-sort histogram + offsets + tile sums
     DevBuf xtab;                                                          // g * omega_ext^i two-level
     uint8_t *vanish_inv = nullptr;
     uint32_t* code = nullptr;
@@ -681,6 +724,29 @@ int bitonic_sort(h2a_ctx* ctx, uint8_t* keys, uint32_t n) {
     return H2A_OK;
 }
 
+int u32_exclusive_scan(h2a_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* sums, uint32_t* total);
+
+// Sorts the u keys at the front of `keys` (n slots, sentinel tail) ascending.  Keys below 2^COUNT_BITS — range tables,
+// selector-gated small inputs — take a counting sort (histogram, prefix, expand); anything else the bitonic network.
+// count_buf: 2 * (2^COUNT_BITS + 1) + 4096 u32 of scratch; stats: 2 u32.
+int sort_keys(h2a_ctx* ctx, uint8_t* keys, uint32_t u, uint32_t n, uint32_t* count_buf, uint32_t* stats) {
+    H2A_CUDA(ctx, cudaMemsetAsync(stats, 0, 8, ctx->stream));
+    LAUNCH1D(dev::key_stats_kernel, ((u + 31) / 32) * 32, 256, keys, u, stats);
+    uint32_t host_stats[2];
+    H2A_CUDA(ctx, cudaMemcpyAsync(host_stats, stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (host_stats[0] != 0 || host_stats[1] >= (1u << dev::COUNT_BITS)) return bitonic_sort(ctx, keys, n);
+    const uint32_t bins = host_stats[1] + 1;
+    uint32_t* hist = count_buf;
+    uint32_t* offsets = count_buf + (1u << dev::COUNT_BITS) + 1;
+    uint32_t* sums = offsets + (1u << dev::COUNT_BITS) + 1;
+    H2A_CUDA(ctx, cudaMemsetAsync(hist, 0, 4ull * bins, ctx->stream));
+    LAUNCH1D(dev::count_keys_kernel, u, 256, keys, u, hist);
+    H2A_TRY(u32_exclusive_scan(ctx, hist, bins, offsets, sums, offsets + bins));
+    LAUNCH1D(dev::expand_counts_kernel, n, 256, offsets, bins, u, n, keys);
+    return H2A_OK;
+}
+
 int u32_exclusive_scan(h2a_ctx* ctx, const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* sums, uint32_t* total) {
     const uint32_t tiles = (n + 2047) / 2048;
     dev::u32_tile_sums_kernel<<<tiles, 256, 0, ctx->stream>>>(in, n, sums);
@@ -744,7 +810,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     const size_t nl = s.lookups.size();
     const size_t n_arrays = 2 * (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * (2 + 6) + 1 + 4 + 1 + 8;
     const size_t m_arrays = (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * 3 + 3 + 2 + 1;
-    p->arena_bytes = 5 * (4ull * n + 8192) + n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
+    p->arena_bytes = 5 * (4ull * n + 8192) + 4ull * (2 * ((1u << dev::COUNT_BITS) + 1) + 8192) + n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
                      sizeof(EvalTables) + sizeof(QuotientArgs);
     H2A_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
     auto poly3 = [&]() { Poly3 q; q.lag = arena_take(p, 32ull * n); q.coef = arena_take(p, 32ull * n); q.ext = arena_take(p, 32ull * m); return q; };
@@ -772,6 +838,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     p->totals = arena_take(p, 32ull * (n / dev::SCAN_TILE + 4096));
     p->small = arena_take(p, 32 * 1024);
     for (int i = 0; i < 5; i++) p->u32buf[i] = (uint32_t*)arena_take(p, 4ull * n + 4096);
+    p->count_buf = (uint32_t*)arena_take(p, 4ull * (2 * ((1u << dev::COUNT_BITS) + 1) + 4096));
     p->vanish_inv = arena_take(p, 32ull * (m / n));
     p->code = (uint32_t*)arena_take(p, code.size() * 4 + 16);
     p->consts = arena_take(p, 32 * s.consts.size() + 32);
@@ -959,8 +1026,8 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             uint32_t *sums = p->u32buf[4], *counters = p->u32buf[4] + (n / 2048 + 8);   // counters: [0] n_rep, [1] n_unused, [2] error
             LAUNCH1D(dev::lookup_keys_kernel, n, 256, l.A, u, n, ka);
             LAUNCH1D(dev::lookup_keys_kernel, n, 256, l.S, u, n, ks);
-            H2A_TRY(bitonic_sort(ctx, ka, n));
-            H2A_TRY(bitonic_sort(ctx, ks, n));
+            H2A_TRY(sort_keys(ctx, ka, u, n, p->count_buf, counters + 4));
+            H2A_TRY(sort_keys(ctx, ks, u, n, p->count_buf, counters + 4));
             LAUNCH1D(dev::fill_u32_kernel, u, 256, unused, u, 1u);
             H2A_CUDA(ctx, cudaMemsetAsync(counters, 0, 16, st));
             LAUNCH1D(dev::lookup_match_kernel, u, 128, ka, ks, u, rep, unused, counters + 2);
