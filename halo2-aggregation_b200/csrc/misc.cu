@@ -239,6 +239,8 @@ int h2a_init(h2a_ctx** out, int device) {
     }
     const char* env = getenv("H2A_MSM_WINDOW");
     if (env) ctx->msm_window_override = atoi(env);
+    env = getenv("H2A_NTT_LOG_TILE");
+    if (env && atoi(env) >= 8 && atoi(env) <= 12) ctx->ntt_log_tile = atoi(env);
     env = getenv("H2A_MSM_SEG");
     if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_seg_len = atoi(env);
     env = getenv("H2A_MSM_ALGO");

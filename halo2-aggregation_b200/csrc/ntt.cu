@@ -31,7 +31,6 @@ struct NttTables {
 namespace {
 
 constexpr int NTT_THREADS = 256;
-constexpr int TILE_ELEMS = 2048;  // elements per block: 64 KB of shared memory
 constexpr int LOG_PW_LO = 10;
 
 struct PassArgs {
@@ -296,8 +295,8 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
     if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
     static bool attr_set = false;
     if (!attr_set) {
-        H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_strided_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_last_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_strided_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_last_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr_set = true;
     }
     NttTables* tab = nullptr;
@@ -346,7 +345,10 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
             a.pw_hi = a.pw_lo + (32ull << LOG_PW_LO);
         }
         const bool last = (p == passes - 1);
-        uint32_t log_tile_max = 11 - std::min(11u, a.s);  // TILE_ELEMS / n_p
+        // measured (tools/sweep.py, H2A_NTT_LOG_TILE): 1024-element tiles (32 KB, 6 blocks per SM by shared memory) beat
+        // 2048 from 2^18 up, 512 wins below
+        const uint32_t log_tile_elems = log_n <= 17 ? std::min<uint32_t>(9, (uint32_t)ctx->ntt_log_tile) : (uint32_t)ctx->ntt_log_tile;
+        uint32_t log_tile_max = log_tile_elems > a.s ? log_tile_elems - a.s : 0;  // tile elements / n_p
         if (!last) {
             a.dst = d_work;
             a.log_tile = std::min(log_tile_max, a.log_r);
