@@ -29,6 +29,7 @@ using h2a_plonk::Shape;
 
 constexpr int MAX_COLS = 64, MAX_Q = 96, MAX_LK = 16, MAX_PERM = 48, MAX_CHUNKS = 24, MAX_PROGS = 96;
 constexpr int LOG_PW = 10;
+constexpr int MAX_EVALS = 512;
 
 // Column tables of one evaluation domain (the 2^k rows, or the 2^ext_k points of the extended coset).
 struct EvalTables {
@@ -274,13 +275,26 @@ __global__ void __launch_bounds__(128) chunk_values_kernel(const uint8_t* coef, 
     if (t * HORNER_L >= n) return;
     chunk_value(coef, n, t, Fr::load(z_)).store(out + 32ull * t);
 }
-// p(z) = sum_t C_t (z^L)^t over the chunk values: one block, strided Horner then a shared-memory tree
-__global__ void __launch_bounds__(256) fold_chunks_kernel(const uint8_t* C, uint32_t nchunks, const uint8_t* z_, uint8_t* out) {
+// All evaluations of a proof in two launches: request r = (coefficients, point, result slot).
+// p(z) = sum_t C_t (z^L)^t over the chunk values: per request one block, strided Horner then a shared-memory tree.
+struct EvalReq {
+    const uint8_t* coef;
+    const uint8_t* z;
+    uint8_t* out;
+};
+__global__ void __launch_bounds__(128) chunk_values_multi_kernel(const EvalReq* reqs, uint32_t n, uint32_t nchunks, uint8_t* chunks) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nchunks) return;
+    const EvalReq r = reqs[blockIdx.y];
+    chunk_value(r.coef, n, t, Fr::load(r.z)).store(chunks + 32ull * ((size_t)blockIdx.y * nchunks + t));
+}
+__global__ void __launch_bounds__(256) fold_chunks_multi_kernel(const EvalReq* reqs, uint32_t nchunks, const uint8_t* chunks) {
     __shared__ __align__(16) uint8_t sh[256 * 32];
-    Fr z = Fr::load(z_), zl = z;
+    const EvalReq r = reqs[blockIdx.x];
+    const uint8_t* C = chunks + 32ull * (size_t)blockIdx.x * nchunks;
+    Fr z = Fr::load(r.z), zl = z;
 #pragma unroll 1
     for (int k = 0; k < 6; k++) zl = zl.sqr();  // z^64
-    // thread j takes chunks j, j+256, ...:  sum_m C_{j+256m} zl^(j+256m) = zl^j * Horner in zl^256
     Fr zb = zl;
 #pragma unroll 1
     for (int k = 0; k < 8; k++) zb = zb.sqr();  // zl^256
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(256) fold_chunks_kernel(const uint8_t* C, uint
         if ((int)threadIdx.x < s) (Fr::load(sh + 32 * threadIdx.x) + Fr::load(sh + 32 * (threadIdx.x + s))).store(sh + 32 * threadIdx.x);
         __syncthreads();
     }
-    if (threadIdx.x == 0) Fr::load(sh).store(out);
+    if (threadIdx.x == 0) Fr::load(sh).store(r.out);
 }
 
 // acc[i] = acc[i] * v + p[i]                       (Horner in v over the polynomials of one rotation set)
@@ -599,6 +613,8 @@ struct ProverState {
     uint8_t *chunks = nullptr, *carries = nullptr, *totals = nullptr, *small = nullptr;
     uint32_t* u32buf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // rep, unused, rep_rank, unused_rank, tile sums / counters
     uint32_t* count_buf = nullptr;                                        // counting-sort histogram + offsets + tile sums
+    uint8_t* eval_chunks = nullptr;                                       // MAX_EVALS x (n / 64) chunk values
+    dev::EvalReq* d_reqs = nullptr;
     DevBuf xtab;                                                          // g * omega_ext^i two-level
     uint8_t *vanish_inv = nullptr;
     uint32_t* code = nullptr;
@@ -690,15 +706,6 @@ int scan_mul(h2a_ctx* ctx, uint8_t* a, uint32_t n, uint8_t* totals) {
         H2A_TRY(scan_mul(ctx, totals, tiles, totals + 32ull * ((tiles + 7) & ~7u)));
         LAUNCH1D(dev::scan_mul_apply_kernel, n, 256, a, n, totals);
     }
-    return H2A_OK;
-}
-
-// value of the polynomial at z (z already on the device at d_z); result lands in d_out (device)
-int eval_poly(h2a_ctx* ctx, ProverState* p, const uint8_t* coef, uint32_t n, const uint8_t* d_z, uint8_t* d_out) {
-    const uint32_t nchunks = (n + dev::HORNER_L - 1) / dev::HORNER_L;
-    LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, coef, n, d_z, p->chunks);
-    dev::fold_chunks_kernel<<<1, 256, 0, ctx->stream>>>(p->chunks, nchunks, d_z, d_out);
-    H2A_LAUNCH_CHECK(ctx);
     return H2A_OK;
 }
 
@@ -810,7 +817,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     const size_t nl = s.lookups.size();
     const size_t n_arrays = 2 * (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * (2 + 6) + 1 + 4 + 1 + 8;
     const size_t m_arrays = (s.n_fixed + s.perm.size() + s.n_advice + s.n_instance + s.n_chunks) + nl * 3 + 3 + 2 + 1;
-    p->arena_bytes = 5 * (4ull * n + 8192) + 4ull * (2 * ((1u << dev::COUNT_BITS) + 1) + 8192) + n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
+    p->arena_bytes = 32ull * MAX_EVALS * (n / dev::HORNER_L + 1) + sizeof(dev::EvalReq) * MAX_EVALS + 8192 + 5 * (4ull * n + 8192) + 4ull * (2 * ((1u << dev::COUNT_BITS) + 1) + 8192) + n_arrays * (32ull * n + 256) + m_arrays * (32ull * m + 256) + (1 << 20) + code.size() * 4 + 64 * s.consts.size() +
                      sizeof(EvalTables) + sizeof(QuotientArgs);
     H2A_CUDA(ctx, cudaMalloc(&p->arena, p->arena_bytes));
     auto poly3 = [&]() { Poly3 q; q.lag = arena_take(p, 32ull * n); q.coef = arena_take(p, 32ull * n); q.ext = arena_take(p, 32ull * m); return q; };
@@ -839,6 +846,8 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     p->small = arena_take(p, 32 * 1024);
     for (int i = 0; i < 5; i++) p->u32buf[i] = (uint32_t*)arena_take(p, 4ull * n + 4096);
     p->count_buf = (uint32_t*)arena_take(p, 4ull * (2 * ((1u << dev::COUNT_BITS) + 1) + 4096));
+    p->eval_chunks = arena_take(p, 32ull * MAX_EVALS * (n / dev::HORNER_L + 1));
+    p->d_reqs = (dev::EvalReq*)arena_take(p, sizeof(dev::EvalReq) * MAX_EVALS);
     p->vanish_inv = arena_take(p, 32ull * (m / n));
     p->code = (uint32_t*)arena_take(p, code.size() * 4 + 16);
     p->consts = arena_take(p, 32 * s.consts.size() + 32);
@@ -1175,11 +1184,22 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     for (auto& l : p->lk) {
         evs.push_back({l.z.coef, 0}); evs.push_back({l.z.coef, 1}); evs.push_back({l.pa.coef, 0}); evs.push_back({l.pa.coef, -1}); evs.push_back({l.ps.coef, 0});
     }
-    if (S_EVAL0 + evs.size() + 8 > 1000) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: too many evaluations");
+    if (S_EVAL0 + evs.size() + 8 > 1000 || evs.size() > (size_t)MAX_EVALS) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: too many evaluations");
     for (auto& e : evs) point_of(e.rot);
     point_of(0);
     for (auto& kv : point_slot) H2A_TRY(upload_fr(ctx, slot(kv.second), rotate_point(s, x, kv.first)));
-    for (size_t i = 0; i < evs.size(); i++) H2A_TRY(eval_poly(ctx, p, evs[i].coef, n, slot(point_slot[evs[i].rot]), slot(S_EVAL0 + (int)i)));
+    {
+        std::vector<dev::EvalReq> reqs(evs.size());
+        for (size_t i = 0; i < evs.size(); i++) reqs[i] = dev::EvalReq{evs[i].coef, slot(point_slot[evs[i].rot]), slot(S_EVAL0 + (int)i)};
+        H2A_CUDA(ctx, cudaMemcpyAsync(p->d_reqs, reqs.data(), sizeof(dev::EvalReq) * reqs.size(), cudaMemcpyHostToDevice, st));
+        H2A_CUDA(ctx, cudaStreamSynchronize(st));   // reqs is a stack-owned vector
+        const uint32_t nch = (n + dev::HORNER_L - 1) / dev::HORNER_L;
+        dim3 grid((nch + 127) / 128, (unsigned)reqs.size());
+        dev::chunk_values_multi_kernel<<<grid, 128, 0, st>>>(p->d_reqs, n, nch, p->eval_chunks);
+        H2A_LAUNCH_CHECK(ctx);
+        dev::fold_chunks_multi_kernel<<<(unsigned)reqs.size(), 256, 0, st>>>(p->d_reqs, nch, p->eval_chunks);
+        H2A_LAUNCH_CHECK(ctx);
+    }
     std::vector<uint8_t> evb(32 * evs.size());
     H2A_CUDA(ctx, cudaMemcpyAsync(evb.data(), slot(S_EVAL0), evb.size(), cudaMemcpyDeviceToHost, st));
     H2A_CUDA(ctx, cudaStreamSynchronize(st));
