@@ -335,31 +335,35 @@ int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void*
     return H2A_OK;
 }
 
+namespace {
+struct ScopedDev {  // device allocation released on every exit path
+    void* p = nullptr;
+    ~ScopedDev() { if (p) cudaFree(p); }
+};
+}  // namespace
+
 static int run_elementwise(h2a_ctx* ctx, int kind, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out,
                            size_t n, size_t elem) {
     if (!ctx || !a || !out) return H2A_ERR_INVALID;
     if (!n) return H2A_OK;
-    void *da = nullptr, *db = nullptr, *dout = nullptr;
-    H2A_CUDA(ctx, cudaMalloc(&da, n * elem));
-    H2A_CUDA(ctx, cudaMalloc(&dout, n * elem));
-    if (b) H2A_CUDA(ctx, cudaMalloc(&db, n * elem));
-    H2A_CUDA(ctx, cudaMemcpyAsync(da, a, n * elem, cudaMemcpyHostToDevice, ctx->stream));
-    if (b) H2A_CUDA(ctx, cudaMemcpyAsync(db, b, n * elem, cudaMemcpyHostToDevice, ctx->stream));
+    ScopedDev da, db, dout;
+    H2A_CUDA(ctx, cudaMalloc(&da.p, n * elem));
+    H2A_CUDA(ctx, cudaMalloc(&dout.p, n * elem));
+    if (b) H2A_CUDA(ctx, cudaMalloc(&db.p, n * elem));
+    H2A_CUDA(ctx, cudaMemcpyAsync(da.p, a, n * elem, cudaMemcpyHostToDevice, ctx->stream));
+    if (b) H2A_CUDA(ctx, cudaMemcpyAsync(db.p, b, n * elem, cudaMemcpyHostToDevice, ctx->stream));
     unsigned blocks = (unsigned)((n + 127) / 128);
     if (kind == 0) {
         if (field == 0)
-            field_op_kernel<FQ><<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da, (uint8_t*)db, (uint8_t*)dout, n);
+            field_op_kernel<FQ><<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da.p, (uint8_t*)db.p, (uint8_t*)dout.p, n);
         else
-            field_op_kernel<FR><<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da, (uint8_t*)db, (uint8_t*)dout, n);
+            field_op_kernel<FR><<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da.p, (uint8_t*)db.p, (uint8_t*)dout.p, n);
     } else {
-        g1_op_kernel<<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da, (uint8_t*)db, (uint8_t*)dout, n);
+        g1_op_kernel<<<blocks, 128, 0, ctx->stream>>>(op, (uint8_t*)da.p, (uint8_t*)db.p, (uint8_t*)dout.p, n);
     }
     H2A_LAUNCH_CHECK(ctx);
-    H2A_CUDA(ctx, cudaMemcpyAsync(out, dout, n * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    H2A_CUDA(ctx, cudaMemcpyAsync(out, dout.p, n * elem, cudaMemcpyDeviceToHost, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(da);
-    cudaFree(dout);
-    if (db) cudaFree(db);
     return H2A_OK;
 }
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {

@@ -293,11 +293,10 @@ size_t smem_bytes_last(uint32_t s, uint32_t log_tile) { return 32ull * ((((1u <<
 int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
                 const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
     if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->ntt_attr_set) {
         H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_strided_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         H2A_CUDA(ctx, cudaFuncSetAttribute(ntt_last_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
+        ctx->ntt_attr_set = true;
     }
     NttTables* tab = nullptr;
     H2A_TRY(get_tables(ctx, log_n, omega, &tab));

@@ -711,10 +711,9 @@ int scan_mul(h2a_ctx* ctx, uint8_t* a, uint32_t n, uint8_t* totals) {
 
 // ascending bitonic sort of n = 2^log_n 256-bit keys in place
 int bitonic_sort(h2a_ctx* ctx, uint8_t* keys, uint32_t n) {
-    static bool attr = false;
-    if (!attr) {
+    if (!ctx->sort_attr_set) {
         H2A_CUDA(ctx, cudaFuncSetAttribute(dev::bitonic_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        attr = true;
+        ctx->sort_attr_set = true;
     }
     for (uint32_t kk = 2; kk <= n; kk <<= 1) {
         uint32_t j = kk >> 1;
