@@ -24,4 +24,4 @@ from .api import (  # noqa: F401
     fr_root_of_unity,
     xorshift_scalar,
 )
-from .dist import allgather_points, allgather_sum, shard_range  # noqa: F401
+from .dist import allgather_points, allgather_sum, make_commitment_exchange, shard_range  # noqa: F401

@@ -394,6 +394,27 @@ class Circuit:
                                                           _ptr(s) if s.size else None, _ptr(_bytes(vk_hash)), _ptr(_bytes(coset_shift))))
         self._keep = (g, g_lagrange)
 
+    def set_distribution(self, rank, world, group=None, device=None):
+        """Column-parallel commitments over `world` processes (torch.distributed): every rank proves the same inputs,
+        commits its share of each batch, and the 64-byte results are allgathered."""
+        if world <= 1:
+            self.ctx._check(self.ctx.lib.h2a_circuit_set_distribution(self.ctx.h, self.h, 0, 1, None, None))
+            self._exchange = None
+            return
+        from .dist import make_commitment_exchange
+        do_exchange = make_commitment_exchange(world, group, device)
+
+        def exchange(_user, buf, m):
+            try:
+                do_exchange(np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), shape=(64 * m,)))
+                return 0
+            except Exception:
+                return -1
+
+        cb = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, c_sz)(exchange)
+        self._exchange = cb   # keep the callback alive
+        self.ctx._check(self.ctx.lib.h2a_circuit_set_distribution(self.ctx.h, self.h, int(rank), int(world), cb, None))
+
     def get_vk(self, n_fixed, n_perm):
         f, s = np.zeros(64 * n_fixed, np.uint8), np.zeros(64 * n_perm, np.uint8)
         self.ctx._check(self.ctx.lib.h2a_circuit_get_vk(self.ctx.h, self.h, _ptr(f), _ptr(s)))

@@ -16,6 +16,11 @@ struct h2a_circuit {
     uint8_t vk_hash[32] = {0};
     bool has_vk = false;
     ProverState* prover = nullptr;
+    // column-parallel commitments: this process commits the columns j with j % world == rank of every
+    // batch and the 64-byte results are exchanged through the caller's collective (NCCL allgather in practice)
+    int dist_rank = 0, dist_world = 1;
+    h2a_exchange_fn dist_exchange = nullptr;
+    void* dist_user = nullptr;
 };
 
 void h2a_prover_state_free(h2a_ctx* ctx, ProverState* p);

@@ -688,10 +688,24 @@ int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint3
 }
 
 // commitments of several device-resident columns over the same bases, pipelined over the two MSM lanes
-int commit_batch(h2a_ctx* ctx, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n, std::vector<hh::PointA>& out) {
-    std::vector<size_t> ns(cols.size(), n);
-    std::vector<uint8_t> pts(64 * cols.size());
-    H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data()));
+int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n,
+                 std::vector<hh::PointA>& out) {
+    std::vector<uint8_t> pts(64 * cols.size(), 0);
+    if (c->dist_world > 1 && c->dist_exchange) {   // this rank's share of the columns, then the exchange
+        std::vector<const uint8_t*> mine;
+        std::vector<size_t> idx;
+        for (size_t j = 0; j < cols.size(); j++)
+            if ((int)(j % (size_t)c->dist_world) == c->dist_rank) { mine.push_back(cols[j]); idx.push_back(j); }
+        std::vector<size_t> ns(mine.size(), n);
+        std::vector<uint8_t> part(64 * mine.size() + 64);
+        if (!mine.empty()) H2A_TRY(h2a_msm_batch_dev(ctx, bases, mine.data(), ns.data(), (int)mine.size(), part.data()));
+        for (size_t q = 0; q < idx.size(); q++) memcpy(pts.data() + 64 * idx[q], part.data() + 64 * q, 64);
+        if (c->dist_exchange(c->dist_user, pts.data(), cols.size()) != 0)
+            H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: the commitment exchange callback failed");
+    } else {
+        std::vector<size_t> ns(cols.size(), n);
+        H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data()));
+    }
     out.resize(cols.size());
     for (size_t i = 0; i < cols.size(); i++) out[i] = hh::affine_load(pts.data() + 64 * i);
     return H2A_OK;
@@ -947,6 +961,15 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     return H2A_OK;
 }
 
+int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* c, int rank, int world, h2a_exchange_fn exchange, void* user) {
+    if (!ctx || !c || world < 1 || rank < 0 || rank >= world) return H2A_ERR_INVALID;
+    c->dist_rank = rank;
+    c->dist_world = world;
+    c->dist_exchange = exchange;
+    c->dist_user = user;
+    return H2A_OK;
+}
+
 int h2a_circuit_get_vk(h2a_ctx* ctx, const h2a_circuit* c, uint8_t* fixed_comms, uint8_t* sigma_comms) {
     if (!ctx || !c) return H2A_ERR_INVALID;
     if (!c->has_vk) H2A_FAIL(ctx, H2A_ERR_INVALID, "get_vk: no key set");
@@ -1013,7 +1036,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             cols.push_back(p->advice[i].lag);
         }
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
         for (uint32_t i = 0; i < s.n_instance; i++) {
             if (!tr.common_point(cms[i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
             if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cms[i]);
@@ -1059,7 +1082,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         std::vector<const uint8_t*> cols;
         for (auto& l : p->lk) { cols.push_back(l.pa.lag); cols.push_back(l.ps.lag); }
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
         for (auto& cm : cms) write_point(cm);
     }
     steps.mark("lookup permuted columns");
@@ -1121,7 +1144,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         for (auto& q : p->pz) cols.push_back(q.lag);
         for (auto& l : p->lk) cols.push_back(l.z.lag);
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
         for (auto& cm : cms) write_point(cm);
     }
     steps.mark("lookup grand products + Z commitments");
@@ -1153,7 +1176,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         std::vector<const uint8_t*> cols;
         for (uint32_t i = 0; i < s.qdeg; i++) cols.push_back(p->h_coef + 32ull * n * i);
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, p->g, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g, cols, n, cms));
         for (auto& cm : cms) write_point(cm);
     }
     steps.mark("h commitments");
@@ -1244,7 +1267,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             const uint8_t* d_z = slot(point_slot[kv.first]);
             if (used == slots) {                                                   // more rotation sets than slots: flush
                 std::vector<hh::PointA> part;
-                H2A_TRY(commit_batch(ctx, p->g, wcols, n, part));
+                H2A_TRY(commit_batch(ctx, c, p->g, wcols, n, part));
                 cms.insert(cms.end(), part.begin(), part.end());
                 wcols.clear();
                 used = 0;
@@ -1257,7 +1280,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             wcols.push_back(q);
         }
         std::vector<hh::PointA> part;
-        H2A_TRY(commit_batch(ctx, p->g, wcols, n, part));
+        H2A_TRY(commit_batch(ctx, c, p->g, wcols, n, part));
         cms.insert(cms.end(), part.begin(), part.end());
         for (auto& cm : cms) write_point(cm);                                      // src/multiopen.rs:392
     }

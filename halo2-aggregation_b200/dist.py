@@ -35,3 +35,23 @@ def allgather_points(partial, group=None, device=None):
 def allgather_sum(partial, group=None, device=None):
     """Sum over ranks of per-rank partial MSM results; every rank returns the same 64 bytes."""
     return g1_sum(allgather_points(partial, group, device))
+
+
+def make_commitment_exchange(world, group=None, device=None):
+    """The `exchange(buf: numpy uint8[64*m])` step of column-parallel proving (h2a_circuit_set_distribution): column j
+    of a batch is owned by rank j % world; after the allgather every rank holds every owner's column."""
+    import torch
+    import torch.distributed as dist
+
+    def exchange(arr):
+        m = arr.size // 64
+        mine = torch.from_numpy(arr.copy())
+        if device is not None:
+            mine = mine.to(device)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine, group=group)
+        allb = torch.stack(out).cpu().numpy()
+        for j in range(m):
+            arr[64 * j:64 * j + 64] = allb[j % world, 64 * j:64 * j + 64]
+
+    return exchange

@@ -190,6 +190,16 @@ size_t h2a_proof_len(const h2a_circuit* circuit);
 int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* circuit, const uint8_t* instance_cols, const uint8_t* advice_cols,
                      const uint8_t* blinds, uint8_t* proof_out, size_t proof_cap, size_t* proof_len,
                      uint8_t* instance_commitments_out /* n_instance*64, may be NULL */);
+/* Column-parallel proving over several GPUs (one process per GPU; every process calls h2a_create_proof with the SAME
+ * inputs): each commitment batch of the prover is split round-robin — this process computes the MSMs of the
+ * columns j with j % world == rank — and `exchange` must then fill in the others.  `exchange(user, buf, m)` receives
+ * m * 64 bytes in which only this rank's columns are set (the rest zero) and must return with every column set by
+ * its owner (rank j % world); an NCCL allgather of the buffers is the intended implementation.  All processes write
+ * byte-identical proofs.  world = 1 or exchange = NULL switches the distribution off. */
+typedef int (*h2a_exchange_fn)(void* user, uint8_t* commitments, size_t m);
+int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* circuit, int rank, int world, h2a_exchange_fn exchange,
+                                 void* user);
+
 /* KZG parameters on the device: g[i] = [s^i] G and g_lagrange[i] = [L_i(s)] G for i < 2^k, what
  * `Setup::<Bn256>::new(k, rng)` builds (examples/simple-example.rs:589, :687) once `rng` has produced the
  * secret `s` (an input here: how the dependency draws it from XorShiftRng is not visible from the reference).

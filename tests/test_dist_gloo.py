@@ -60,3 +60,36 @@ def test_single_process_passthrough(orc):
     import halo2_aggregation_b200 as h2a
     p = orc.gen_bases(4, 1)
     assert bytes(h2a.allgather_sum(p)) == bytes(p)
+
+
+def _exchange_worker(rank, world, port, m, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import halo2_aggregation_b200 as h2a
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    buf = np.zeros(64 * m, np.uint8)
+    for j in range(m):
+        if j % world == rank:
+            buf[64 * j:64 * j + 64] = (j * 7 + 1) % 251        # this rank's columns
+    h2a.make_commitment_exchange(world)(buf)
+    q.put((rank, bytes(buf)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,m", [(2, 5), (3, 4)])
+def test_column_parallel_commitment_exchange(world, m):
+    """Host logic of h2a_circuit_set_distribution: after the exchange every rank holds every owner's column."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, m, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = b"".join(bytes([(j * 7 + 1) % 251]) * 64 for j in range(m))
+    assert all(r[1] == want for r in results)

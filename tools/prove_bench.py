@@ -125,6 +125,9 @@ def run(ctx, args):
     t0 = time.perf_counter()
     circ.set_keys(g, gl, fixed_b, sigmas_b, fr(ctx, [0xC0FFEE]), fr(ctx, [7]))
     t_keys = time.perf_counter() - t0
+    world = getattr(args, "world", 1)
+    if world > 1:   # column-parallel commitments: every rank proves the same inputs and commits its share
+        circ.set_distribution(args.rank, world, device="cuda")
     blinds = random_blinds(ctx, circ.blinds_len(), 3)
     try:        # witness columns in pinned host memory, as a caller that owns its buffers would arrange
         import torch
@@ -154,7 +157,7 @@ def run(ctx, args):
                                              "9 permutation columns (3 chunks), degree 5, ext domain 2^%d; witness columns in %s host memory" %
                                              (shape.num_fixed, args.lookups, args.k + 2, "pinned" if pinned else "pageable"),
                                  "msm_tables": args.precompute},
-                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys})
+                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof)})
 
 
 def main():
@@ -164,9 +167,32 @@ def main():
     ap.add_argument("--lookups", type=int, default=9)
     ap.add_argument("--precompute", type=int, default=-1, help="window bits of the per-Params MSM tables (0 = none)")
     args = ap.parse_args()
-    ctx = h2a.Context(0)
+    args.rank, local_rank, args.world = (int(os.environ.get(v, d)) for v, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    if args.world > 1:   # torchrun: one process per GPU, commitments column-parallel over the ranks
+        import hashlib
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = h2a.Context(local_rank)
     res = run(ctx, args)
-    print(json.dumps(res), flush=True)
+    res["n_gpus"] = args.world
+    if args.world > 1:
+        t = torch.tensor([res["value"]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["value"] = float(t[0])
+        digest = torch.tensor(list(hashlib.sha256(res.pop("proof_digest_src")).digest()), dtype=torch.uint8, device="cuda")
+        alld = [torch.empty_like(digest) for _ in range(args.world)]
+        dist.all_gather(alld, digest)
+        res["proofs_identical_across_ranks"] = all(bool((d == alld[0]).all()) for d in alld)
+        res["config"]["distribution"] = "commitments column-parallel over %d GPUs (64-byte results allgathered with NCCL); everything else replicated" % args.world
+    else:
+        res.pop("proof_digest_src", None)
+    if args.rank == 0:
+        print(json.dumps(res), flush=True)
+    if args.world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if not res["proof_verifies"]:
         sys.exit("proof does not satisfy the pairing relation")
 
