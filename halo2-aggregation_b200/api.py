@@ -211,6 +211,9 @@ class Context:
     def set_msm_algorithm(self, algo):
         self._check(self.lib.h2a_msm_set_algorithm(self.h, int(algo)))
 
+    def set_msm_host_split(self, pieces):
+        self._check(self.lib.h2a_msm_set_host_split(self.h, int(pieces)))
+
     def msm(self, bases, scalars, offset=0):
         """best_multiexp over resident bases, host scalars.  Returns the 64-byte affine result."""
         scalars = _bytes(scalars)

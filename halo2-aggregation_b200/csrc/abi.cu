@@ -1,6 +1,9 @@
 // abi.cu — the MSM / NTT entry points of include/h2agg.h: argument checks, host<->device staging,
 // and dispatch to the kernels in msm.cu / ntt.cu.
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ctx.hpp"
 #include "host_bn254.hpp"
@@ -89,12 +92,78 @@ int h2a_msm_set_algorithm(h2a_ctx* ctx, int algo) {
     return H2A_OK;
 }
 
+int h2a_msm_set_host_split(h2a_ctx* ctx, int pieces) {
+    if (!ctx || pieces < 1 || pieces > 16) return H2A_ERR_INVALID;
+    ctx->msm_host_split = pieces;
+    return H2A_OK;
+}
+
 int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
                    uint8_t out_affine[64]) {
     if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;
     if (offset > bases->n || n > bases->n - offset)
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
     return h2a_msm_run(ctx, bases, offset, (const uint8_t*)d_scalars, n, out_affine);
+}
+
+// A large MSM whose scalars sit in host memory is cut into point ranges that alternate between the two lanes: while
+// one range is sorted and accumulated, the next range's scalars cross PCIe.  The copies are chained (one at a time on
+// the link), each range yields a canonical affine partial, and the partials are added on the host in range order.
+static int msm_host_split(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
+                          uint8_t out_affine[64]) {
+    h2a_ctx* alt = nullptr;
+    H2A_TRY(h2a_get_alt(ctx, &alt));
+    alt->msm_window_override = ctx->msm_window_override;
+    alt->msm_algo = ctx->msm_algo;
+    h2a_ctx* lanes[2] = {ctx, alt};
+    const int pieces = ctx->msm_host_split;
+    // the first range is the only one whose copy is exposed: it gets a smaller share, the rest is cut evenly
+    int first_pct = 100 / pieces;
+    if (const char* env = getenv("H2A_MSM_HOST_FIRST_PCT")) first_pct = std::max(1, std::min(99, atoi(env)));
+    const size_t first_len = std::min(n, (n * (size_t)first_pct / 100 + 1023) & ~(size_t)1023);
+    const size_t piece_len = pieces > 1 ? (n - first_len + pieces - 2) / (pieces - 1) : 0;
+    std::vector<uint8_t> partials((size_t)pieces * 64, 0);
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    for (int l = 0; l < 2; l++) H2A_CUDA(ctx, cudaEventCreateWithFlags(&copied[l], cudaEventDisableTiming));
+    H2A_CUDA(ctx, cudaEventRecord(copied[1], ctx->stream));   // the second lane starts after work already queued here
+    H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, copied[1], 0));
+    int pending_piece[2] = {-1, -1};
+    const bool prof = ctx->profiling;
+    ctx->profiling = false;
+    int rc = H2A_OK;
+    for (int j = 0; j < pieces && rc == H2A_OK; j++) {
+        const size_t lo = j == 0 ? 0 : std::min(n, first_len + (size_t)(j - 1) * piece_len);
+        const size_t len = j == 0 ? first_len : std::min(n - lo, piece_len);
+        h2a_ctx* lane = lanes[j & 1];
+        if (pending_piece[j & 1] >= 0) {
+            rc = h2a_msm_finish(lane, partials.data() + 64 * pending_piece[j & 1]);
+            pending_piece[j & 1] = -1;
+            if (rc != H2A_OK) break;
+        }
+        rc = h2a_reserve(lane, lane->scalars, len * 32 + 32);
+        if (rc == H2A_OK && len) {
+            cudaError_t e = cudaSuccess;
+            if (j > 0) e = cudaStreamWaitEvent(lane->stream, copied[(j - 1) & 1], 0);   // one copy on the link at a time
+            if (e == cudaSuccess) e = cudaMemcpyAsync(lane->scalars.p, scalars + 32 * lo, len * 32, cudaMemcpyHostToDevice, lane->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(copied[j & 1], lane->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = H2A_ERR_CUDA; }
+        }
+        if (rc == H2A_OK) rc = h2a_msm_launch(lane, bases, offset + lo, (const uint8_t*)lane->scalars.p, len);
+        if (rc == H2A_OK) pending_piece[j & 1] = j;
+        else if (lane != ctx) ctx->err = lane->err;
+    }
+    for (int l = 0; l < 2; l++) {
+        if (pending_piece[l] >= 0) {
+            int r2 = h2a_msm_finish(lanes[l], partials.data() + 64 * pending_piece[l]);
+            if (rc == H2A_OK) rc = r2;
+        }
+        cudaEventDestroy(copied[l]);
+    }
+    ctx->profiling = prof;
+    ctx->launches += alt->launches;
+    alt->launches = 0;
+    if (rc != H2A_OK) return rc;
+    return h2a_g1_sum(partials.data(), (size_t)pieces, out_affine);
 }
 
 int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
@@ -106,6 +175,7 @@ int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_
         memset(out_affine, 0, 64);
         return H2A_OK;
     }
+    if (n >= ((size_t)1 << 21) && ctx->msm_host_split > 1) return msm_host_split(ctx, bases, offset, scalars, n, out_affine);
     H2A_TRY(h2a_reserve(ctx, ctx->scalars, n * 32));
     H2A_CUDA(ctx, cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return h2a_msm_run(ctx, bases, offset, (const uint8_t*)ctx->scalars.p, n, out_affine);

@@ -31,6 +31,7 @@ struct h2a_ctx {
     bool ntt_attr_set = false, sort_attr_set = false;  // cudaFuncSetAttribute done for this ctx's device
     int ntt_log_tile = 10;  // log2 of the elements one NTT block holds in shared memory (32 B each)
     int msm_seg_len = 32;  // buckets per thread in the segmented bucket reduction
+    int msm_host_split = 2;  // point ranges a large host-scalar MSM is cut into so copies overlap compute (1 = off)
     int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
     // profiling

@@ -95,6 +95,9 @@ int h2a_msm_set_window(h2a_ctx* ctx, int c);
 /* Bucket accumulation algorithm: 1 (default) pairwise tree of batched affine additions; 0 serial XYZZ mixed
  * additions with one thread per bucket task.  Same result bit for bit; for A/B measurement and tests. */
 int h2a_msm_set_algorithm(h2a_ctx* ctx, int algo);
+/* h2a_msm_g1 with >= 2^21 host scalars is cut into `pieces` point ranges so that the scalar copy of one range
+ * overlaps the computation of the previous one (default 2; 1 = one copy then one MSM).  Same result bit for bit. */
+int h2a_msm_set_host_split(h2a_ctx* ctx, int pieces);
 
 /* ---- Fr NTT ------------------------------------------------------------------------------
  * Replaces halo2 `arithmetic::best_fft(a, omega, log_n)` and the `EvaluationDomain` methods

@@ -284,6 +284,13 @@ def test_msm_linearity_at_bench_size(ctx):
     hb.precompute(20)
     assert bytes(ctx.msm_dev(hb, ds, n)) == bytes(full)
     assert bytes(ctx.msm_dev(hb, ds + 32 * half, half, offset=half)) == bytes(hi)
+    # host scalars: the call cuts the MSM into point ranges whose copies overlap compute (h2a_msm_set_host_split)
+    host_scalars = ctx.d2h(ds, 32 * n)
+    for pieces in (2, 3, 1):
+        ctx.set_msm_host_split(pieces)
+        assert bytes(ctx.msm(hb, host_scalars)) == bytes(full)
+        assert bytes(ctx.msm(hb, host_scalars[32 * half:], offset=half)) == bytes(hi)
+    ctx.set_msm_host_split(2)
     m = 1 << 16
     ones = np.frombuffer(pm.fr_mont_bytes(1) * m, dtype=np.uint8)
     pts = ctx.d2h(db, 64 * m)
