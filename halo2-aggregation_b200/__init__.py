@@ -13,6 +13,7 @@ from .api import (  # noqa: F401
     Circuit,
     serialize_shape,
     Transcript,
+    PermutationAssembly,
     EvaluationDomain,
     H2AError,
     best_multiexp,

@@ -64,6 +64,8 @@ def load_library():
     lib.h2a_prove_phase_name.restype = ctypes.c_char_p
     lib.h2a_transcript_new.restype = ctypes.c_void_p
     lib.h2a_transcript_free.restype = None
+    lib.h2a_assembly_free.restype = None
+    lib.h2a_assembly_free.argtypes = [ctypes.c_void_p]
     _LIB = lib
     return lib
 
@@ -488,6 +490,44 @@ class Bases:
         if self.h:
             self.ctx._check(self.ctx.lib.h2a_bases_free(self.ctx.h, self.h))
             self.h = None
+
+
+class PermutationAssembly:
+    """The copy-constraint bookkeeping of key generation (`keygen_vk` / `keygen_pk`,
+    examples/simple-example.rs:593-594): `copy` joins the cycles of two cells of the permutation columns,
+    `sigmas` evaluates the sigma columns on the device (h2a_assembly_*)."""
+
+    def __init__(self, n_cols, k):
+        self.lib = load_library()
+        self.n_cols, self.k = int(n_cols), int(k)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.h2a_assembly_new(ctypes.c_uint32(self.n_cols), ctypes.c_uint32(self.k), ctypes.byref(self.h))
+        if rc != 0:
+            raise H2AError(rc, "h2a_assembly_new")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.h2a_assembly_free(self.h)
+            self.h = None
+
+    def copy(self, col_a, row_a, col_b, row_b):
+        rc = self.lib.h2a_assembly_copy(self.h, ctypes.c_uint32(col_a), ctypes.c_uint32(row_a), ctypes.c_uint32(col_b),
+                                        ctypes.c_uint32(row_b))
+        if rc != 0:
+            raise H2AError(rc, "h2a_assembly_copy: cell outside the permutation columns")
+
+    def mapping(self):
+        out = np.zeros(self.n_cols << self.k, np.uint32)
+        rc = self.lib.h2a_assembly_mapping(self.h, out.ctypes.data_as(ctypes.c_void_p))
+        if rc != 0:
+            raise H2AError(rc, "h2a_assembly_mapping")
+        return out
+
+    def sigmas(self, ctx, omega, delta):
+        """n_cols columns of 2^k elements (32-byte Montgomery), the `sigmas` argument of Circuit.set_keys."""
+        out = np.zeros((self.n_cols << self.k) * 32, np.uint8)
+        ctx._check(self.lib.h2a_assembly_sigmas(ctx.h, self.h, _ptr(_bytes(omega)), _ptr(_bytes(delta)), _ptr(out)))
+        return out
 
 
 class Transcript:

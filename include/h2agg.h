@@ -203,6 +203,22 @@ typedef int (*h2a_exchange_fn)(void* user, uint8_t* commitments, size_t m);
 int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* circuit, int rank, int world, h2a_exchange_fn exchange,
                                  void* user);
 
+/* ---- Key generation: copy constraints -> sigma columns -------------------------------------
+ * The permutation part of `keygen_vk` / `keygen_pk` (examples/simple-example.rs:593-594, :696-697).  An assembly
+ * holds one permutation over the cells (col, row) of the n_cols permutation columns (`vk.permutation`,
+ * src/verifier.rs:244-259), initially the identity; h2a_assembly_copy joins the cycles of two cells, as the layouter
+ * does for every copy constraint (host bookkeeping).  h2a_assembly_sigmas evaluates on the device
+ *   sigma[col][row] = delta^{col'} * omega^{row'},  (col', row') = the cell that follows (col, row) in its cycle,
+ * (delta: `Fr::DELTA`, src/permutation.rs:259) and writes n_cols columns of 2^k elements — the `sigmas` argument of
+ * h2a_circuit_set_keys.  h2a_assembly_mapping returns the permutation itself (next cell = col' * 2^k + row'). */
+typedef struct h2a_assembly h2a_assembly;
+int h2a_assembly_new(uint32_t n_cols, uint32_t k, h2a_assembly** out);
+void h2a_assembly_free(h2a_assembly* assembly);
+int h2a_assembly_copy(h2a_assembly* assembly, uint32_t col_a, uint32_t row_a, uint32_t col_b, uint32_t row_b);
+int h2a_assembly_mapping(const h2a_assembly* assembly, uint32_t* out_next_cell /* n_cols * 2^k */);
+int h2a_assembly_sigmas(h2a_ctx* ctx, const h2a_assembly* assembly, const uint8_t omega[32], const uint8_t delta[32],
+                        uint8_t* out_sigmas /* n_cols * 2^k * 32 */);
+
 /* KZG parameters on the device: g[i] = [s^i] G and g_lagrange[i] = [L_i(s)] G for i < 2^k, what
  * `Setup::<Bn256>::new(k, rng)` builds (examples/simple-example.rs:589, :687) once `rng` has produced the
  * secret `s` (an input here: how the dependency draws it from XorShiftRng is not visible from the reference).

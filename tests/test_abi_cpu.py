@@ -95,3 +95,44 @@ def test_argument_errors_without_a_device():
     assert lib.h2a_init(None, 0) == -1
     assert lib.h2a_destroy(None) == -1
     assert lib.h2a_blinds_len(None) == 0 and lib.h2a_proof_len(None) == 0
+
+
+def test_permutation_assembly_cycles():
+    """Host bookkeeping of key generation (h2a_assembly_copy): the mapping stays a permutation and its cycles are
+    exactly the classes of the copy constraints, whatever the order and redundancy of the copies."""
+    rng = random.Random(5)
+    n_cols, k = 5, 6
+    n = 1 << k
+    asm = h2a.PermutationAssembly(n_cols, k)
+    assert list(asm.mapping()) == list(range(n_cols * n))
+    parent = list(range(n_cols * n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    for _ in range(400):
+        a, b = rng.randrange(n_cols * n), rng.randrange(n_cols * n)
+        if rng.random() < 0.3:
+            b = a                                     # a cell copied to itself changes nothing
+        asm.copy(a // n, a % n, b // n, b % n)
+        parent[find(a)] = find(b)
+    nxt = [int(v) for v in asm.mapping()]
+    assert sorted(nxt) == list(range(n_cols * n))
+    seen = set()
+    for start in range(n_cols * n):
+        if start in seen:
+            continue
+        cyc, c = [], start
+        while c not in seen:
+            seen.add(c); cyc.append(c); c = nxt[c]
+        assert c == start
+        cls = find(start)
+        assert all(find(x) == cls for x in cyc)
+        assert len(cyc) == sum(1 for x in range(n_cols * n) if find(x) == cls)
+    with pytest.raises(h2a.H2AError):
+        asm.copy(n_cols, 0, 0, 0)
+    with pytest.raises(h2a.H2AError):
+        asm.copy(0, n, 0, 0)

@@ -165,3 +165,33 @@ def test_large_proof_verifies(ctx, orc, k):
     res2 = pk.verify_proof(shape, to_pts(fc), to_pts(sc), 77, to_pts(inst2), proof2)
     assert not pk.pairing_relation_holds(res2, s)
     circ.free(); g.free(); gl.free()
+
+
+def test_keygen_sigmas_from_copy_constraints(ctx, orc):
+    """Row a11: the permutation assembly's sigma columns are delta^col' * omega^row' of its own mapping, and a proof
+    made with them verifies (the copy constraints of the sample circuit hold in its witness)."""
+    k = 7
+    c = circuits.my_circuit(k=k, table_bits=4)
+    shape = c["shape"]
+    m = len(shape.perm_columns)
+    asm = h2a.PermutationAssembly(m, k)
+    for cyc in c["cycles"]:
+        for (ca, ra), (cb, rb) in zip(cyc, cyc[1:]):
+            asm.copy(ca, ra, cb, rb)
+    nxt = asm.mapping()
+    got = asm.sigmas(ctx, frs_bytes([shape.omega]), frs_bytes([pk.DELTA]))
+    n = 1 << k
+    om = [pow(shape.omega, i, pm.R) for i in range(n)]
+    want = [pow(pk.DELTA, int(v) >> k, pm.R) * om[int(v) & (n - 1)] % pm.R for v in nxt]
+    assert bytes(got) == bytes(frs_bytes(want))
+    # the same equivalence classes as the oracle's cycle list, so both sigma sets accept the same witnesses
+    s = 0x5eed5eed5eed
+    g, gl = ctx.kzg_setup(k, frs_bytes([s]))
+    circ = h2a.Circuit(ctx, shape, frs_bytes(shape.constants))
+    circ.set_keys(g, gl, cols_bytes(c["fixed"]), got, frs_bytes([5]), frs_bytes([shape.coset_shift]))
+    proof, inst = circ.prove(cols_bytes(c["instance"]), cols_bytes(c["advice"]), frs_bytes(pk.blinds_buffer(shape, 3)))
+    fc, sc = circ.get_vk(shape.num_fixed, m)
+    to_pts = lambda b: [pm.affine_from_bytes(b[64 * i:64 * i + 64]) for i in range(len(b) // 64)]
+    res = pk.verify_proof(shape, to_pts(fc), to_pts(sc), 5, to_pts(inst), proof)
+    assert pk.pairing_relation_holds(res, s)
+    circ.free(); g.free(); gl.free()
