@@ -134,10 +134,10 @@ __global__ void field_op_kernel(int op, const uint8_t* a, const uint8_t* b, uint
         case 1: r = x - y; break;
         case 2: r = x * y; break;
         case 3: r = x.sqr(); break;
-        case 4: r = x.inv(); break;
+        case 4: r = x.inv_fermat(); break;
         case 6: r = x.to_mont(); break;
         case 7: r = x.from_mont(); break;
-        case 8: r = x.inv_fast(); break;
+        case 8: r = x.inv(); break;
         default: r = x.neg(); break;
     }
     r.store(out + 32 * i);

@@ -250,8 +250,9 @@ int h2a_gen_scalars_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, voi
 int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out /* n*64 */);
 
 /* ---- test / measurement hooks ---------------------------------------------------------- */
-/* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inv 5 neg
- * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer, 8 inverse by binary Euclid. */
+/* Element-wise device field arithmetic: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 inverse by Fermat (cross-check) 5 neg
+ * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer, 8 inverse by division steps
+ * (the one every kernel uses). */
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);

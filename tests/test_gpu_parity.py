@@ -44,7 +44,14 @@ def test_field_ops(ctx, orc, field, mod):
     for op in ("add", "sub", "mul", "sqr", "neg"):
         assert bytes(ctx.field_op(field, op, am, bm)) == bytes(orc.field_op(field, op, am, bm)), op
     assert bytes(ctx.field_op(field, "inv", am[:32 * 64])) == bytes(orc.field_op(field, "inv", am[:32 * 64]))
-    assert bytes(ctx.field_op(field, "inv_fast", am[:32 * 2000])) == bytes(orc.field_op(field, "inv", am[:32 * 2000]))
+    assert bytes(ctx.field_op(field, "inv_fast", am)) == bytes(orc.field_op(field, "inv", am))
+    # values with long runs of zero / one bits, small values and their negatives (division-step corner cases)
+    special = [1 << i for i in range(254)] + [(mod - (1 << i)) % mod for i in range(254)] + [(1 << i) - 1 for i in range(1, 254)]
+    special = [v % mod for v in special] + list(range(0, 64)) + [mod - i for i in range(1, 64)]
+    sm = orc.to_mont(field, ints_to_bytes(special))
+    assert bytes(ctx.field_op(field, "inv_fast", sm)) == bytes(orc.field_op(field, "inv", sm))
+    raw = ints_to_bytes(special)   # the same integers taken as Montgomery representatives
+    assert bytes(ctx.field_op(field, "inv_fast", raw)) == bytes(orc.field_op(field, "inv", raw))
     # all pairs of edge values through mul
     e = edge(mod)
     aa = orc.to_mont(field, ints_to_bytes([x for x in e for _ in e]))
