@@ -30,7 +30,8 @@ struct h2a_ctx {
     int msm_window_override = 0;
     bool ntt_attr_set = false, sort_attr_set = false;  // cudaFuncSetAttribute done for this ctx's device
     int ntt_log_tile = 10;  // log2 of the elements one NTT block holds in shared memory (32 B each)
-    int msm_seg_len = 32;  // buckets per thread in the segmented bucket reduction
+    int msm_red_chunk = 2048;  // segments per block at level 2 of the bucket reduction (power of two)
+    int msm_seg_len = 16;  // buckets per thread at level 1 of the bucket reduction (power of two)
     int msm_host_split = 2;  // point ranges a large host-scalar MSM is cut into so copies overlap compute (1 = off)
     int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
@@ -53,6 +54,7 @@ struct h2a_ctx {
         bool pre = false;
         int c = 0;
         uint32_t groups = 0;
+        uint32_t log_l = 0;  // log2 of the reduction's segment length (the host finishes the single-window Horner)
     } msm_pending;
     h2a_ctx* alt = nullptr;  // second lane (own stream + workspace) for pipelined batches; created on first use
 

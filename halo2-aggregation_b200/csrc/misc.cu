@@ -243,6 +243,8 @@ int h2a_init(h2a_ctx** out, int device) {
     if (env && atoi(env) >= 8 && atoi(env) <= 12) ctx->ntt_log_tile = atoi(env);
     env = getenv("H2A_MSM_SEG");
     if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_seg_len = atoi(env);
+    env = getenv("H2A_MSM_RED_CHUNK");
+    if (env && atoi(env) >= 128 && atoi(env) <= 65536 && (atoi(env) & (atoi(env) - 1)) == 0) ctx->msm_red_chunk = atoi(env);
     env = getenv("H2A_MSM_HOST_SPLIT");
     if (env && atoi(env) >= 1 && atoi(env) <= 16) ctx->msm_host_split = atoi(env);
     env = getenv("H2A_MSM_ALGO");

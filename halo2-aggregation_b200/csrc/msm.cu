@@ -495,54 +495,44 @@ __global__ void __launch_bounds__(128) msm_accumulate_pts_kernel(const uint8_t* 
     acc.store(partial + 128ull * t);
 }
 
-// ---- segment reduction: segment `seg` of window `w` covers buckets [lo, lo+L) (0-based; bucket t
-// weighs t+1).  out = sum_t (t+1) * bucket[t] = (running-sum result) + lo * (plain sum).
+// ---- bucket reduction: window total = sum_t (t+1) * bucket[t].  A single thread's point addition is a chain of
+// dependent Montgomery products (~7 us), so the phase is latency-bound and organised for few additions in series:
+//   level 1  one thread per segment j of L = 2^log_l buckets: S_j = plain sum, T_j = sum_i (i+1) * bucket[jL+i]
+//            (running sum, 2L additions in series; L = 16 measured best against L = 4, 8, 32 — a variant issuing the
+//            two additions of a step interleaved in one thread needed 246 registers and was no faster)
+//   level 2  total = sum_j T_j + L * sum_j j * S_j, and sum_j j * S_j = sum_b 2^b * P_b with
+//            P_b = sum of the S_j whose index has bit b set: plain tree sums, one block per (window, b, chunk)
+//   level 3  tree over the chunks
+//   level 4  (several windows) 2^(b + log_l) * P_b by doublings, one thread per bit, and the sum over the bits;
+//            with a single window the host finishes the 17-point Horner itself.
 // Bucket k's value is partial[task_off[k]] (identity when the bucket has no task).
-__global__ void __launch_bounds__(64) msm_reduce_segments_kernel(const uint8_t* __restrict__ partial,
-                                                                 const uint32_t* __restrict__ task_off,
-                                                                 uint32_t n_windows, uint32_t buckets_per_window,
-                                                                 uint32_t seg_len, uint8_t* __restrict__ seg_out) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t segs = buckets_per_window / seg_len;
-    if (t >= n_windows * segs) return;
-    uint32_t w = t / segs, seg = t % segs, lo = seg * seg_len;
-    const uint32_t k0 = w * buckets_per_window + lo;
-    XYZZ run = XYZZ::identity(), acc = XYZZ::identity();
-    for (int i = (int)seg_len - 1; i >= 0; i--) {
-        const uint32_t t0 = task_off[k0 + i], t1 = task_off[k0 + i + 1];
-        if (t1 > t0) {
-            XYZZ b = XYZZ::load(partial + 128ull * t0);
-            xyzz_add_nl(run, b);
-        }
+
+__device__ __forceinline__ XYZZ load_bucket(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ task_off, uint32_t k) {
+    const uint32_t t0 = task_off[k], t1 = task_off[k + 1];
+    return t1 > t0 ? XYZZ::load(partial + 128ull * t0) : XYZZ::identity();
+}
+__global__ void __launch_bounds__(128) msm_reduce_l1_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ task_off,
+                                                            uint32_t total_segs, uint32_t log_l, uint8_t* __restrict__ s_out,
+                                                            uint8_t* __restrict__ t_out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_segs) return;
+    const uint32_t k0 = t << log_l;
+    XYZZ run = load_bucket(partial, task_off, k0 + (1u << log_l) - 1u), acc = XYZZ::identity();
+    for (int i = (int)(1u << log_l) - 2; i >= 0; i--) {
         xyzz_add_nl(acc, run);
+        const XYZZ b = load_bucket(partial, task_off, k0 + (uint32_t)i);
+        xyzz_add_nl(run, b);
     }
-    if (lo != 0 && !run.is_identity()) {  // acc += lo * run  (double-and-add, lo < 2^24)
-        XYZZ m = XYZZ::identity();
-        for (int bit = 31 - __clz(lo); bit >= 0; bit--) {
-            m = m.dbl();
-            if ((lo >> bit) & 1) xyzz_add_nl(m, run);
-        }
-        xyzz_add_nl(acc, m);
-    }
-    acc.store(seg_out + 128ull * t);
+    xyzz_add_nl(acc, run);
+    run.store(s_out + 128ull * t);
+    acc.store(t_out + 128ull * t);
 }
 
-// ---- per-window sum of segment results: one block per window, tree in shared memory
-constexpr int WIN_THREADS = 128;
-// (a "window" here is a group of `segs` consecutive segment sums: one Pippenger window, or a slice of the
-// single shared window when the bases carry precomputed tables)
-__global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8_t* __restrict__ seg_in, uint32_t segs,
-                                                                     uint8_t* __restrict__ win_out) {
-    __shared__ __align__(16) uint8_t sh[WIN_THREADS * 128];
-    uint32_t w = blockIdx.x;
-    XYZZ acc = XYZZ::identity();
-    for (uint32_t s = threadIdx.x; s < segs; s += WIN_THREADS) {
-        XYZZ b = XYZZ::load(seg_in + 128ull * ((size_t)w * segs + s));
-        xyzz_add_nl(acc, b);
-    }
+constexpr int RED_THREADS = 128;
+__device__ __forceinline__ XYZZ block_tree_sum(XYZZ acc, uint8_t* sh) {
     acc.store(sh + 128 * threadIdx.x);
     __syncthreads();
-    for (int stride = WIN_THREADS / 2; stride > 0; stride >>= 1) {
+    for (int stride = RED_THREADS / 2; stride > 0; stride >>= 1) {
         if ((int)threadIdx.x < stride) {
             XYZZ a = XYZZ::load(sh + 128 * threadIdx.x), b = XYZZ::load(sh + 128 * (threadIdx.x + stride));
             xyzz_add_nl(a, b);
@@ -550,7 +540,50 @@ __global__ void __launch_bounds__(WIN_THREADS) msm_window_sum_kernel(const uint8
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) XYZZ::load(sh).store(win_out + 128ull * w);
+    return XYZZ::load(sh);
+}
+// grid (chunks, windows * (nbits + 1)); q < nbits: P_q restricted to the chunk; q == nbits: the chunk's sum of T
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_l2_kernel(const uint8_t* __restrict__ s_in, const uint8_t* __restrict__ t_in,
+                                                                    uint32_t segs, uint32_t nbits, uint32_t chunk_len,
+                                                                    uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t sh[RED_THREADS * 128];
+    const uint32_t w = blockIdx.y / (nbits + 1u), q = blockIdx.y % (nbits + 1u), ch = blockIdx.x;
+    const uint8_t* src = (q == nbits ? t_in : s_in) + 128ull * ((size_t)w * segs);
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t j = ch * chunk_len + threadIdx.x; j < (ch + 1u) * chunk_len; j += RED_THREADS) {
+        if (q == nbits || ((j >> q) & 1u)) {
+            XYZZ b = XYZZ::load(src + 128ull * j);
+            xyzz_add_nl(acc, b);
+        }
+    }
+    acc = block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) acc.store(out + 128ull * ((size_t)blockIdx.y * gridDim.x + ch));
+}
+// one block per (window, q): sum of the chunk partials
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_l3_kernel(const uint8_t* __restrict__ in, uint32_t chunks,
+                                                                    uint8_t* __restrict__ out) {
+    __shared__ __align__(16) uint8_t sh[RED_THREADS * 128];
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t c = threadIdx.x; c < chunks; c += RED_THREADS) {
+        XYZZ b = XYZZ::load(in + 128ull * ((size_t)blockIdx.x * chunks + c));
+        xyzz_add_nl(acc, b);
+    }
+    acc = block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) acc.store(out + 128ull * blockIdx.x);
+}
+// one block per window: T + sum_b 2^(b + log_l) * P_b
+__global__ void __launch_bounds__(RED_THREADS) msm_reduce_l4_kernel(const uint8_t* __restrict__ in, uint32_t nbits, uint32_t log_l,
+                                                                    uint8_t* __restrict__ win_out) {
+    __shared__ __align__(16) uint8_t sh[RED_THREADS * 128];
+    const uint32_t q = threadIdx.x;
+    XYZZ acc = XYZZ::identity();
+    if (q <= nbits) {
+        acc = XYZZ::load(in + 128ull * ((size_t)blockIdx.x * (nbits + 1u) + q));
+        if (q < nbits)
+            for (uint32_t d = 0; d < q + log_l; d++) acc = acc.dbl();
+    }
+    acc = block_tree_sum(acc, sh);
+    if (threadIdx.x == 0) acc.store(win_out + 128ull * blockIdx.x);
 }
 
 int pick_window(size_t n) {  // from the measured sweep (tools/sweep.py --windows ...), B200
@@ -569,11 +602,15 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     const uint32_t nb = (uint32_t)BW * B;
     if ((uint64_t)n * W >= (1ull << 32) || (PRE && (uint64_t)stride * W >= (1ull << 31)))
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
-    const uint32_t seg_len = std::max(1u, std::min((uint32_t)ctx->msm_seg_len, B / 32u));
-    const uint32_t segs = B / seg_len;
-    // groups of segment sums returned to the host: one per window, or (PRE) 64 slices of the single window
-    const uint32_t groups = PRE ? std::min(64u, segs) : (uint32_t)W;
-    const uint32_t segs_per_group = (uint32_t)BW * segs / groups;
+    // bucket reduction geometry (see msm_reduce_l1_kernel): segments of 2^log_l buckets, chunks of <= 2048 segments
+    uint32_t log_l = 0;
+    while ((2u << log_l) <= (uint32_t)ctx->msm_seg_len && (2u << log_l) <= B / 4u) log_l++;
+    const uint32_t segs = B >> log_l;                 // per window
+    uint32_t nbits = 0;
+    while ((1u << nbits) < segs) nbits++;
+    const uint32_t chunk_len = std::min(segs, (uint32_t)ctx->msm_red_chunk), chunks = segs / chunk_len;
+    // points returned to the host: one per window, or (PRE) the nbits + 1 level sums of the single window
+    const uint32_t groups = PRE ? nbits + 1u : (uint32_t)W;
     const uint32_t scan_blocks = (nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
     // task length: twice the mean bucket load (uniformly distributed digits then give one task per bucket while
     // the fuller buckets fed by a narrow top window are cut into a few equal tasks), shorter when buckets are scarce
@@ -593,7 +630,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     H2A_TRY(h2a_reserve(ctx, ctx->heavy, ((size_t)max_multi + 1) * 4));              // multi_list
     H2A_TRY(h2a_reserve(ctx, ctx->sorted, n * (size_t)W * 4));
     H2A_TRY(h2a_reserve(ctx, ctx->buckets, (size_t)max_tasks * 128));                // per-task partial sums
-    H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)BW * segs * 128));
+    H2A_TRY(h2a_reserve(ctx, ctx->segsums, (size_t)BW * segs * 256 + (size_t)BW * (nbits + 1) * (chunks + 1) * 128));   // S, T, chunk partials, level sums
     H2A_TRY(h2a_reserve(ctx, ctx->winsums, (size_t)groups * 128));
     H2A_TRY(h2a_reserve_pinned(ctx, (size_t)groups * 128));
     uint32_t* offsets = (uint32_t*)ctx->offsets.p;
@@ -727,16 +764,32 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     msm_merge_light_kernel<<<(max_multi + 127) / 128, 128, 0, st>>>(task_off, multi_list, n_multi, partial);
     H2A_LAUNCH_CHECK(ctx);
     h2a_prof_mark(ctx);
-    msm_reduce_segments_kernel<<<(BW * segs + 63) / 64, 64, 0, st>>>(partial, task_off, BW, B, seg_len, (uint8_t*)ctx->segsums.p);
-    H2A_LAUNCH_CHECK(ctx);
-    msm_window_sum_kernel<<<groups, WIN_THREADS, 0, st>>>((const uint8_t*)ctx->segsums.p, segs_per_group, (uint8_t*)ctx->winsums.p);
-    H2A_LAUNCH_CHECK(ctx);
+    {
+        uint8_t* s_buf = (uint8_t*)ctx->segsums.p;
+        uint8_t* t_buf = s_buf + (size_t)BW * segs * 128;
+        uint8_t* chunk_buf = t_buf + (size_t)BW * segs * 128;
+        uint8_t* level_buf = chunk_buf + (size_t)BW * (nbits + 1) * chunks * 128;
+        msm_reduce_l1_kernel<<<(BW * segs + 127) / 128, 128, 0, st>>>(partial, task_off, BW * segs, log_l, s_buf, t_buf);
+        H2A_LAUNCH_CHECK(ctx);
+        uint8_t* l2_out = chunks > 1 ? chunk_buf : (PRE ? (uint8_t*)ctx->winsums.p : level_buf);
+        msm_reduce_l2_kernel<<<dim3(chunks, BW * (nbits + 1)), RED_THREADS, 0, st>>>(s_buf, t_buf, segs, nbits, chunk_len, l2_out);
+        H2A_LAUNCH_CHECK(ctx);
+        if (chunks > 1) {
+            msm_reduce_l3_kernel<<<BW * (nbits + 1), RED_THREADS, 0, st>>>(chunk_buf, chunks, PRE ? (uint8_t*)ctx->winsums.p : level_buf);
+            H2A_LAUNCH_CHECK(ctx);
+        }
+        if (!PRE) {
+            msm_reduce_l4_kernel<<<BW, RED_THREADS, 0, st>>>(level_buf, nbits, log_l, (uint8_t*)ctx->winsums.p);
+            H2A_LAUNCH_CHECK(ctx);
+        }
+    }
     h2a_prof_mark(ctx);
     H2A_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->winsums.p, (size_t)groups * 128, cudaMemcpyDeviceToHost, st));
     ctx->msm_pending.active = true;
     ctx->msm_pending.pre = PRE;
     ctx->msm_pending.c = C;
     ctx->msm_pending.groups = groups;
+    ctx->msm_pending.log_l = log_l;
     return H2A_OK;
 }
 
@@ -776,8 +829,11 @@ int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]) {
     using namespace h2a_host;
     const uint8_t* ws = (const uint8_t*)ctx->pinned;
     PointX acc = px_identity();
-    if (ctx->msm_pending.pre) {  // the tables already carry the 2^(c*w) factors: plain sum of the slices
-        for (uint32_t g = 0; g < ctx->msm_pending.groups; g++) acc = px_add(acc, px_load(ws + 128 * g));
+    if (ctx->msm_pending.pre) {  // single window (the tables carry the 2^(c*w) factors): T + 2^log_l * sum_b 2^b P_b
+        const uint32_t nbits = ctx->msm_pending.groups - 1;
+        for (int b = (int)nbits - 1; b >= 0; b--) acc = px_add(px_dbl(acc), px_load(ws + 128 * b));
+        for (uint32_t i = 0; i < ctx->msm_pending.log_l; i++) acc = px_dbl(acc);
+        acc = px_add(acc, px_load(ws + 128 * nbits));
     } else {                     // Horner over the window sums: acc = acc * 2^c + S_w, top window first
         for (int w = (int)ctx->msm_pending.groups - 1; w >= 0; w--) {
             for (int i = 0; i < ctx->msm_pending.c; i++) acc = px_dbl(acc);
