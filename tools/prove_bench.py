@@ -156,6 +156,9 @@ def run(ctx, args):
                       "config": {"workload": "prover pipeline, synthetic aggregation-circuit profile (SURVEY §7): 8 advice, %d fixed, %d lookups, "
                                              "9 permutation columns (3 chunks), degree 5, ext domain 2^%d; witness columns in %s host memory" %
                                              (shape.num_fixed, args.lookups, args.k + 2, "pinned" if pinned else "pageable"),
+                                 "scalars": "advice values are range-checked small integers (they sit in the lookup table, as the limb columns of the "
+                                            "aggregation circuit do), so their commitments see mostly-zero windows; the permuted, grand-product, quotient "
+                                            "and opening polynomials are full-width field elements",
                                  "msm_tables": args.precompute},
                       "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof)})
 
