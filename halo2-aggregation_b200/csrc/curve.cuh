@@ -19,6 +19,12 @@ struct Affine {  // identity <=> (0, 0)   ((0,0) is not on the curve: b = 3)
         a.y = Fq::load((const uint8_t*)p + 32);
         return a;
     }
+    __device__ __forceinline__ static Affine load_gather(const void* p) {   // see Fp::load_gather
+        Affine a;
+        a.x = Fq::load_gather(p);
+        a.y = Fq::load_gather((const uint8_t*)p + 32);
+        return a;
+    }
     __device__ __forceinline__ void store(void* p) const {
         x.store(p);
         y.store((uint8_t*)p + 32);

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __re
     XYZZ acc = XYZZ::identity();
     if (j < end) {
         uint32_t e = sorted[j];
-        Affine p = Affine::load(bases + 64ull * (e & 0x7fffffffu));
+        Affine p = Affine::load_gather(bases + 64ull * (e & 0x7fffffffu));
         for (;;) {
             ++j;
             uint32_t e_next = 0;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint8_t* __re
             const bool more = j < end;
             if (more) {
                 e_next = sorted[j];
-                p_next = Affine::load(bases + 64ull * (e_next & 0x7fffffffu));
+                p_next = Affine::load_gather(bases + 64ull * (e_next & 0x7fffffffu));
             }
             if (!p.is_identity()) acc.add_affine(p, (e >> 31) != 0);
             if (!more) break;
@@ -348,7 +348,7 @@ __device__ __forceinline__ Affine load_input(const uint8_t* __restrict__ bases, 
         const uint32_t e = sorted[i];
         Affine p;
         if (e == 0xffffffffu) { p.x = Fq::zero(); p.y = Fq::zero(); return p; }   // padding slot
-        p = Affine::load(bases + 64ull * (e & 0x7fffffffu));
+        p = Affine::load_gather(bases + 64ull * (e & 0x7fffffffu));
         if ((e >> 31) && !p.is_identity()) p.y = p.y.neg();
         return p;
     }
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restr
         }
         bool slow = pad_slot;
         if (!slow) {
-            Fq x1 = Fq::load(a1), x2 = Fq::load(a2);
+            Fq x1 = FIRST ? Fq::load_gather(a1) : Fq::load(a1), x2 = FIRST ? Fq::load_gather(a2) : Fq::load(a2);
             d = x2 - x1;
             slow = x1.is_zero() || x2.is_zero() || d.is_zero();
         }
