@@ -434,7 +434,6 @@ struct Fp {
         }
         return out * (r2() * r2());
     }
-    __device__ __forceinline__ Fp inv_fast() const { return inv(); }
 
     // is canonical-integer limb vector v >= modulus ?
     __device__ __forceinline__ static bool geq_mod(const uint32_t* v) {

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restr
     run.store(totals + 32ull * t);
 }
 // in-place inversion of the chunk totals, INV_T per thread with one field inversion (second level of Montgomery's
-// trick).  The kernel is a pure latency chain, hence the short batch and the binary-Euclid inversion.
+// trick).  The kernel is a pure latency chain, hence the short batch; Fq::inv is branch-free (division steps).
 constexpr uint32_t INV_T = 16;
 __global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restrict__ totals, uint32_t count) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, lo = t * INV_T;
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restri
         pre[q] = run;
         run = run * Fq::load(totals + 32ull * (lo + q));
     }
-    Fq inv = run.inv_fast();
+    Fq inv = run.inv();
     for (uint32_t q = cnt; q-- > 0;) {
         Fq v = Fq::load(totals + 32ull * (lo + q));
         (inv * pre[q]).store(totals + 32ull * (lo + q));

@@ -305,6 +305,26 @@ def test_msm_linearity_at_bench_size(ctx):
     hb.free(); ctx.dev_free(db); ctx.dev_free(ds)
 
 
+def test_msm_largest_baseline_size(ctx):
+    """2^24 points (the top of BASELINE's sweep): the MSM equals the sum of the MSMs over its four quarters, with and
+    without window tables, and a host-scalar call (split into point ranges) gives the same element."""
+    n = 1 << 24
+    db, ds = ctx.dev_alloc(64 * n), ctx.dev_alloc(32 * n)
+    ctx.gen_bases_dev(5, n, db)
+    ctx.gen_scalars_dev(6, n, ds)
+    hb = ctx.bases_from_device(db, n)
+    q = n // 4
+    parts = [ctx.msm_dev(hb, ds + 32 * q * i, q, offset=q * i) for i in range(4)]
+    want = bytes(h2a.g1_sum(np.concatenate(parts)))
+    assert want != bytes(64)
+    assert bytes(ctx.msm_dev(hb, ds, n)) == want
+    hb.precompute(20)
+    assert bytes(ctx.msm_dev(hb, ds, n)) == want
+    host_scalars = ctx.d2h(ds, 32 * n)
+    assert bytes(ctx.msm(hb, host_scalars)) == want
+    hb.free(); ctx.dev_free(db); ctx.dev_free(ds)
+
+
 # ------------------------------------------------------------------ NTT
 @pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 10, 11, 12, 13, 16, 20, 21])
 def test_ntt_matches_oracle(ctx, orc, k):
