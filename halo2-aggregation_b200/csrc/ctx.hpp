@@ -120,5 +120,6 @@ int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c);
 int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n);
 int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]);
 // m MSMs over the same bases with device-resident scalars, pipelined over two lanes
-int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m, uint8_t* out_affine);
+int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m, uint8_t* out_affine,
+                      const uint8_t* const* h_src = nullptr);
 int h2a_get_alt(h2a_ctx* ctx, h2a_ctx** out);

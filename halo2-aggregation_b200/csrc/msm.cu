@@ -855,10 +855,16 @@ int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8
 // Two lanes alternate: while lane A's latency-bound tail (bucket reduction, window sums, copy back) drains, lane B's
 // histogram / scatter / accumulation kernels already occupy the SMs.  Lane B first waits for everything queued on the
 // main stream, so scalars produced there by earlier kernels are complete.
+// h_src (optional): column j is first copied from host memory h_src[j] into d_scalars[j] on its lane's stream, so the
+// copy of one column overlaps the computation of the previous one.
 int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m,
-                      uint8_t* out_affine) {
+                      uint8_t* out_affine, const uint8_t* const* h_src) {
     if (m <= 0) return H2A_OK;
-    if (m == 1) return h2a_msm_run(ctx, bases, 0, d_scalars[0], n[0], out_affine);
+    if (m == 1) {
+        if (h_src && h_src[0] && n[0])
+            H2A_CUDA(ctx, cudaMemcpyAsync((void*)d_scalars[0], h_src[0], 32 * n[0], cudaMemcpyHostToDevice, ctx->stream));
+        return h2a_msm_run(ctx, bases, 0, d_scalars[0], n[0], out_affine);
+    }
     h2a_ctx* alt = nullptr;
     H2A_TRY(h2a_get_alt(ctx, &alt));
     alt->msm_window_override = ctx->msm_window_override;
@@ -878,6 +884,10 @@ int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const
             rc = h2a_msm_finish(lane, out_affine + 64 * pending_col[j & 1]);
             pending_col[j & 1] = -1;
             if (rc != H2A_OK) break;
+        }
+        if (h_src && h_src[j] && n[j]) {
+            cudaError_t e = cudaMemcpyAsync((void*)d_scalars[j], h_src[j], 32 * n[j], cudaMemcpyHostToDevice, lane->stream);
+            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = H2A_ERR_CUDA; break; }
         }
         rc = h2a_msm_launch(lane, bases, 0, d_scalars[j], n[j]);
         if (rc == H2A_OK) pending_col[j & 1] = j;

@@ -688,10 +688,15 @@ int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint3
 }
 
 // commitments of several device-resident columns over the same bases, pipelined over the two MSM lanes
+// (host_src, optional: column j is still in host memory there and is copied into cols[j] on the way, overlapped with the
+// previous column's MSM)
 int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n,
-                 std::vector<hh::PointA>& out) {
+                 std::vector<hh::PointA>& out, const std::vector<const uint8_t*>* host_src = nullptr) {
     std::vector<uint8_t> pts(64 * cols.size(), 0);
     if (c->dist_world > 1 && c->dist_exchange) {   // this rank's share of the columns, then the exchange
+        if (host_src)   // every rank needs every column on its device later: copy them all first
+            for (size_t j = 0; j < cols.size(); j++)
+                H2A_CUDA(ctx, cudaMemcpyAsync((void*)cols[j], (*host_src)[j], 32ull * n, cudaMemcpyHostToDevice, ctx->stream));
         std::vector<const uint8_t*> mine;
         std::vector<size_t> idx;
         for (size_t j = 0; j < cols.size(); j++)
@@ -704,7 +709,7 @@ int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, con
             H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: the commitment exchange callback failed");
     } else {
         std::vector<size_t> ns(cols.size(), n);
-        H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data()));
+        H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data(), host_src ? host_src->data() : nullptr));
     }
     out.resize(cols.size());
     for (size_t i = 0; i < cols.size(); i++) out[i] = hh::affine_load(pts.data() + 64 * i);
@@ -1026,17 +1031,17 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
 
     tr.common_scalar(hh::fr_load(c->vk_hash));                                     // src/verifier.rs:341-358
     {   // instance (:360-363) and advice (:365-376) commitments in one pipelined batch
-        std::vector<const uint8_t*> cols;
+        std::vector<const uint8_t*> cols, src;
         for (uint32_t i = 0; i < s.n_instance; i++) {
-            H2A_CUDA(ctx, cudaMemcpyAsync(p->instance[i].lag, instance_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+            src.push_back(instance_cols + 32ull * n * i);
             cols.push_back(p->instance[i].lag);
         }
         for (uint32_t i = 0; i < s.n_advice; i++) {
-            H2A_CUDA(ctx, cudaMemcpyAsync(p->advice[i].lag, advice_cols + 32ull * n * i, 32ull * n, cudaMemcpyHostToDevice, st));
+            src.push_back(advice_cols + 32ull * n * i);
             cols.push_back(p->advice[i].lag);
         }
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms, &src));
         for (uint32_t i = 0; i < s.n_instance; i++) {
             if (!tr.common_point(cms[i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
             if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cms[i]);
