@@ -22,8 +22,9 @@ using namespace h2a;
 
 __device__ __noinline__ void xyzz_add_fn(XYZZ& a, const XYZZ& b) { a.add(b); }
 
-// One block per output sum; each thread multiplies its terms by double-and-add over the canonical
-// scalar, the block folds the partial sums in shared memory, thread 0 normalises to affine.
+// One block per output sum; each thread multiplies its terms with signed 4-bit windows over the canonical scalar
+// (8-entry table, 65 windows of 4 doublings + at most one addition: the chain of ~256 doublings is the latency floor
+// of a variable-base product), the block folds the partial sums in shared memory, thread 0 normalises to affine.
 constexpr int SMALL_THREADS = 64;
 __global__ void __launch_bounds__(SMALL_THREADS) small_msm_kernel(const uint8_t* __restrict__ bases,
                                                                   const uint8_t* __restrict__ scalars,
@@ -36,15 +37,34 @@ __global__ void __launch_bounds__(SMALL_THREADS) small_msm_kernel(const uint8_t*
         Affine p = Affine::load(bases + 64ull * i);
         if (p.is_identity()) continue;
         Fr s = Fr::load(scalars + 32ull * i).from_mont();
-        XYZZ base = XYZZ::from_affine(p), m = XYZZ::identity();
-        int top = -1;
-#pragma unroll
-        for (int k = 7; k >= 0; k--)
-            if (top < 0 && s.l[k]) top = 32 * k + 31 - __clz(s.l[k]);
-        // s.l is indexed dynamically below: keep it in local memory by design (tiny kernel)
-        for (int bit = top; bit >= 0; bit--) {
-            m = m.dbl();
-            if ((s.l[bit >> 5] >> (bit & 31)) & 1) xyzz_add_fn(m, base);
+        // signed digits d_w in [-8, 8), s = sum_w d_w 16^w; the table and the digits live in local memory by design
+        int8_t dig[65];
+        int carry = 0, top = -1;
+        for (int w = 0; w < 64; w++) {
+            int d = (int)((s.l[w >> 3] >> (4 * (w & 7))) & 15u) + carry;
+            carry = d >= 8;
+            d -= carry << 4;
+            dig[w] = (int8_t)d;
+            if (d) top = w;
+        }
+        dig[64] = (int8_t)carry;
+        if (carry) top = 64;
+        XYZZ tab[8];   // tab[k] = (k + 1) P
+        tab[0] = XYZZ::from_affine(p);
+        for (int k = 1; k < 8; k++) {
+            tab[k] = tab[k - 1];
+            xyzz_add_fn(tab[k], tab[0]);
+        }
+        XYZZ m = XYZZ::identity();
+        for (int w = top; w >= 0; w--) {
+            if (w != top)
+                for (int k = 0; k < 4; k++) m = m.dbl();
+            const int d = dig[w];
+            if (d) {
+                XYZZ t = tab[(d > 0 ? d : -d) - 1];
+                if (d < 0) t.y = t.y.neg();
+                xyzz_add_fn(m, t);
+            }
         }
         xyzz_add_fn(acc, m);
     }

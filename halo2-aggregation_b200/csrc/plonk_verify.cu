@@ -3,7 +3,10 @@
 // lookup expressions, expected h(x), the query list — and hands ALL sums of the GWC accumulation
 // (src/multiopen.rs:271-509), with H flattened into its pieces (src/vanishing.rs:177-188), to one launch of
 // the small-MSM kernel.  Output: (e, f, w, zw), the `[G1Affine; 4]` of examples/simple-example.rs:620,668-671.
+#include <algorithm>
 #include <cstring>
+#include <string>
+#include <thread>
 
 #include "host_glue.hpp"
 #include "plonk.hpp"
@@ -61,8 +64,13 @@ struct Reader {
     }
 };
 
-// One proof -> its (e, f, w, zw) term lists appended to `tl`.
-int collect_terms(h2a_ctx* ctx, const h2a_circuit* c, const uint8_t* inst_comms, const uint8_t* proof, size_t len,
+// error text of one proof's replay (the proofs of a batch are replayed by several host threads)
+struct ErrSink {
+    std::string err;
+};
+
+// One proof -> its (e, f, w, zw) term lists appended to `tl`.  Host only; touches nothing shared but `c` (read-only).
+int collect_terms(ErrSink* ctx, const h2a_circuit* c, const uint8_t* inst_comms, const uint8_t* proof, size_t len,
                   const uint8_t g1[64], h2a_glue::TermList& tl) {
     const Shape& s = c->shape;
     h2a_glue::Transcript tr;
@@ -261,9 +269,35 @@ int h2a_verify_proof_batch(h2a_ctx* ctx, const h2a_circuit* c, size_t n_proofs, 
     if (!c->has_vk) H2A_FAIL(ctx, H2A_ERR_INVALID, "verify: no verifying key set (h2a_circuit_set_vk / h2a_circuit_set_keys)");
     uint8_t g1[64];
     affine_store(g1, PointA{fq_one(), Fq{el_from_u64(2, MOD_Q)}});
+    // transcript replay, point decompression (one square root per point) and expression evaluation are independent per
+    // proof: spread them over the host cores, then evaluate all 4 * n_proofs sums in one launch
+    std::vector<h2a_glue::TermList> lists(n_proofs);
+    std::vector<ErrSink> errs(n_proofs);
+    std::vector<int> rcs(n_proofs, H2A_OK);
+    auto replay = [&](size_t first, size_t step) {
+        for (size_t i = first; i < n_proofs; i += step)
+            rcs[i] = collect_terms(&errs[i], c, inst_comms + 64 * (size_t)c->shape.n_instance * i, proofs[i], proof_lens[i], g1, lists[i]);
+    };
+    const size_t workers = n_proofs < 4 ? 1 : std::min<size_t>({n_proofs, (size_t)std::max(1u, std::thread::hardware_concurrency()), 32});
+    if (workers <= 1) {
+        replay(0, 1);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < workers; t++) pool.emplace_back(replay, t, workers);
+        replay(0, workers);
+        for (auto& th : pool) th.join();
+    }
     h2a_glue::TermList tl;
-    for (size_t i = 0; i < n_proofs; i++)
-        H2A_TRY(collect_terms(ctx, c, inst_comms + 64 * (size_t)c->shape.n_instance * i, proofs[i], proof_lens[i], g1, tl));
+    for (size_t i = 0; i < n_proofs; i++) {
+        if (rcs[i] != H2A_OK) {
+            ctx->err = errs[i].err;
+            return rcs[i];
+        }
+        const uint32_t base = (uint32_t)(tl.bases.size() / 64);
+        tl.bases.insert(tl.bases.end(), lists[i].bases.begin(), lists[i].bases.end());
+        tl.scalars.insert(tl.scalars.end(), lists[i].scalars.begin(), lists[i].scalars.end());
+        for (size_t q = 1; q < lists[i].offsets.size(); q++) tl.offsets.push_back(base + lists[i].offsets[q]);
+    }
     return h2a_small_msm(ctx, tl.bases.data(), tl.scalars.data(), tl.offsets.data(), 4 * n_proofs, out_efwzw);
 }
 

@@ -60,6 +60,11 @@ def main():
         proofs.append(proof); insts.append(inst)
     barrier()
     t_prove = time.perf_counter() - t0
+    if proofs:   # first call of the process pays module load and local-memory pool growth: keep it out of the timing
+        t0 = time.perf_counter()
+        circ.verify_batch(np.concatenate(insts[:1]), proofs[:1])
+        t_first = time.perf_counter() - t0
+    barrier()
     t0 = time.perf_counter()
     mine = circ.verify_batch(np.concatenate(insts), proofs) if proofs else np.zeros((0, 256), np.uint8)
     if world > 1:
