@@ -369,25 +369,38 @@ __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restr
     }
     Fq run = Fq::one();
     uint32_t o = base_o + lane;
-#pragma unroll 1
-    for (int j = 0; j < AFF_B && o < n_out; j++, o += 32u) {
-        // the denominator of a generic addition needs the two x coordinates only: fetch the y halves just for the
-        // rare cases (an identity / padding slot, equal x) that pair_case has to tell apart
-        Fq d;
+    // the denominator of a generic addition needs the two x coordinates only (the y halves are fetched just for the rare
+    // cases — an identity / padding slot, equal x — that pair_case has to tell apart); the x pair of the NEXT output is
+    // requested before the current one is consumed, so two gathers per thread are in flight
+    Fq x1, x2;
+    bool pad_slot = false;
+    auto fetch = [&](uint32_t oo, Fq& f1, Fq& f2, bool& pad) {
         const uint8_t *a1, *a2;
-        bool pad_slot = false;
+        pad = false;
         if (FIRST) {
-            const uint32_t e1 = sorted[2u * o], e2 = sorted[2u * o + 1u];
-            pad_slot = e1 == 0xffffffffu || e2 == 0xffffffffu;
+            const uint32_t e1 = sorted[2u * oo], e2 = sorted[2u * oo + 1u];
+            pad = e1 == 0xffffffffu || e2 == 0xffffffffu;
             a1 = bases + 64ull * (e1 & 0x7fffffffu);
             a2 = bases + 64ull * (e2 & 0x7fffffffu);
         } else {
-            a1 = in_pts + 128ull * o;
+            a1 = in_pts + 128ull * oo;
             a2 = a1 + 64;
         }
+        if (!pad) {
+            f1 = FIRST ? Fq::load_gather(a1) : Fq::load(a1);
+            f2 = FIRST ? Fq::load_gather(a2) : Fq::load(a2);
+        }
+    };
+    if (o < n_out) fetch(o, x1, x2, pad_slot);
+#pragma unroll 1
+    for (int j = 0; j < AFF_B && o < n_out; j++, o += 32u) {
+        Fq n1, n2;
+        bool npad = false;
+        const bool more = j + 1 < (int)AFF_B && o + 32u < n_out;
+        if (more) fetch(o + 32u, n1, n2, npad);
+        Fq d;
         bool slow = pad_slot;
         if (!slow) {
-            Fq x1 = FIRST ? Fq::load_gather(a1) : Fq::load(a1), x2 = FIRST ? Fq::load_gather(a2) : Fq::load(a2);
             d = x2 - x1;
             slow = x1.is_zero() || x2.is_zero() || d.is_zero();
         }
@@ -397,6 +410,7 @@ __global__ void __launch_bounds__(128) aff_forward_kernel(const uint8_t* __restr
         }
         run.store(scratch + 32ull * (((size_t)warp * AFF_B + j) * 32u + lane));
         run = run * d;
+        x1 = n1; x2 = n2; pad_slot = npad;
     }
     run.store(totals + 32ull * t);
 }
@@ -422,7 +436,7 @@ __global__ void __launch_bounds__(64) aff_invert_totals_kernel(uint8_t* __restri
 }
 // backward pass: individual inverses from the inverted chunk total, finish the additions
 template <bool FIRST>
-__global__ void __launch_bounds__(128) aff_backward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, 6) aff_backward_kernel(const uint8_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                            const uint8_t* __restrict__ in_pts, uint32_t n_out,
                                                            const uint32_t* __restrict__ total_slots, uint32_t o0, int round,
                                                            const uint8_t* __restrict__ scratch, const uint8_t* __restrict__ totals,
