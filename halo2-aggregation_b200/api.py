@@ -267,11 +267,15 @@ class Context:
         self._check(self.lib.h2a_ntt_dev(self.h, ctypes.c_void_p(d_a), ctypes.c_uint32(log_n), _ptr(_bytes(omega)),
                                          int(bool(inverse)), _ptr(cs)))
 
-    def coeff_to_extended(self, coeffs, k, ext_k, coset_shift):
+    def coeff_to_extended(self, coeffs, k, ext_k, coset_shift, out=None):
+        """`out`: optional caller buffer of 32 << ext_k bytes (e.g. pinned memory), as the C ABI takes it."""
         coeffs = _bytes(coeffs)
         if coeffs.size != 32 << k:
             raise H2AError(-1, "coeff_to_extended: buffer has %d bytes, expected %d" % (coeffs.size, 32 << k))
-        out = np.zeros(32 << ext_k, np.uint8)
+        if out is None:
+            out = np.empty(32 << ext_k, np.uint8)
+        elif out.dtype != np.uint8 or out.size != 32 << ext_k or not out.flags["C_CONTIGUOUS"]:
+            raise H2AError(-1, "coeff_to_extended: out must be a contiguous uint8 buffer of %d bytes" % (32 << ext_k))
         self._check(self.lib.h2a_coeff_to_extended(self.h, _ptr(coeffs), ctypes.c_uint32(k), ctypes.c_uint32(ext_k),
                                                    _ptr(_bytes(coset_shift)), _ptr(out)))
         return out

@@ -80,7 +80,21 @@ def main():
         kern_ms = sum(ph.values())
         print(json.dumps({"op": "ntt_fr", "log_n": k, "ms": ms, "kernel_ms": kern_ms, "melem_per_s": n / ms / 1e3,
                           "algo_gbs": 64 * n / (kern_ms * 1e-3) / 1e9, "phases_ms": ph}), flush=True)
+        # the other transforms of EvaluationDomain: inverse (+ 1/n), coset forward / inverse (zeta-distribute convention)
+        zeta = ctx.field_op(1, "to_mont", np.frombuffer((7).to_bytes(32, "little"), dtype=np.uint8)).copy()
+        for name, inv, shift in (("intt_fr", True, None), ("coset_ntt_fr", False, zeta), ("coset_intt_fr", True, zeta)):
+            ms = timeit(lambda: ctx.ntt_dev(d.data_ptr(), k, w, inverse=inv, coset_shift=shift), args.reps)
+            kern_ms = sum(dict(ctx.last_phases(1)).values())
+            print(json.dumps({"op": name, "log_n": k, "ms": ms, "kernel_ms": kern_ms, "melem_per_s": n / ms / 1e3}), flush=True)
         del d
+        if k + 2 <= 24:   # coeff_to_extended n -> 4n through the host-buffer entry point (copies inside the time)
+            coeffs = torch.empty(32 * n, dtype=torch.uint8).pin_memory()
+            coeffs.numpy()[:] = 0
+            coeffs.numpy()[::32] = 1
+            ext = torch.empty(128 * n, dtype=torch.uint8).pin_memory()
+            ms = timeit(lambda: ctx.coeff_to_extended(coeffs.numpy(), k, k + 2, zeta, out=ext.numpy()), max(2, args.reps // 2))
+            print(json.dumps({"op": "coeff_to_extended_host", "log_n": k, "ext_log_n": k + 2, "ms": ms,
+                              "note": "h2a_coeff_to_extended with host buffers: pinned host buffers, H2D of n and D2H of 4n elements inside the time"}), flush=True)
     ctx.close()
 
 
