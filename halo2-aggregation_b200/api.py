@@ -280,6 +280,13 @@ class Context:
                                                    _ptr(_bytes(coset_shift)), _ptr(out)))
         return out
 
+    def coeff_to_extended_dev(self, d_coeffs, k, ext_k, coset_shift, d_out):
+        self._check(self.lib.h2a_coeff_to_extended_dev(self.h, ctypes.c_void_p(d_coeffs), ctypes.c_uint32(k), ctypes.c_uint32(ext_k),
+                                                       _ptr(_bytes(coset_shift)), ctypes.c_void_p(d_out)))
+
+    def extended_to_coeff_dev(self, d_ext, ext_k, coset_shift):
+        self._check(self.lib.h2a_extended_to_coeff_dev(self.h, ctypes.c_void_p(d_ext), ctypes.c_uint32(ext_k), _ptr(_bytes(coset_shift))))
+
     def extended_to_coeff(self, ext, ext_k, coset_shift):
         ext = _bytes(ext).copy()
         self._check(self.lib.h2a_extended_to_coeff(self.h, _ptr(ext), ctypes.c_uint32(ext_k), _ptr(_bytes(coset_shift))))

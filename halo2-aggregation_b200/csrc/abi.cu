@@ -313,6 +313,28 @@ int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint3
     return H2A_OK;
 }
 
+int h2a_coeff_to_extended_dev(h2a_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k, const uint8_t coset_shift[32],
+                              void* d_out) {
+    if (!ctx || !d_coeffs || !d_out || !coset_shift) return H2A_ERR_INVALID;
+    if (k < 1 || ext_k < k || ext_k > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "coeff_to_extended: k=%u ext_k=%u", k, ext_k);
+    const size_t in_bytes = 32ull << k, out_bytes = 32ull << ext_k;
+    const uint8_t *lo = (const uint8_t*)d_coeffs, *out = (const uint8_t*)d_out;
+    if (lo < out + out_bytes && out < lo + in_bytes) H2A_FAIL(ctx, H2A_ERR_INVALID, "coeff_to_extended: input and output overlap");
+    H2A_TRY(h2a_reserve(ctx, ctx->ntt_a, out_bytes));
+    uint8_t omega[32];
+    h2a_fr_root_of_unity(ext_k, omega);
+    H2A_TRY(h2a_ntt_run(ctx, lo, 1u << k, (uint8_t*)ctx->ntt_a.p, (uint8_t*)d_out, ext_k, omega, 0, coset_shift));
+    H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return H2A_OK;
+}
+
+int h2a_extended_to_coeff_dev(h2a_ctx* ctx, void* d_ext, uint32_t ext_k, const uint8_t coset_shift[32]) {
+    if (!ctx || !d_ext || !coset_shift) return H2A_ERR_INVALID;
+    uint8_t omega[32];
+    if (ext_k < 1 || h2a_fr_root_of_unity(ext_k, omega) != H2A_OK) H2A_FAIL(ctx, H2A_ERR_INVALID, "extended_to_coeff: ext_k=%u", ext_k);
+    return h2a_ntt_dev(ctx, d_ext, ext_k, omega, 1, coset_shift);
+}
+
 int h2a_extended_to_coeff(h2a_ctx* ctx, uint8_t* ext, uint32_t ext_k, const uint8_t coset_shift[32]) {
     if (!ctx || !ext || !coset_shift) return H2A_ERR_INVALID;
     uint8_t omega[32];

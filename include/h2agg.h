@@ -118,6 +118,10 @@ int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint3
                           const uint8_t coset_shift[32], uint8_t* out /* 2^ext_k * 32 */);
 /* extended_to_coeff: 2^ext_k coset evaluations -> 2^ext_k coefficients (caller truncates). In place. */
 int h2a_extended_to_coeff(h2a_ctx* ctx, uint8_t* ext, uint32_t ext_k, const uint8_t coset_shift[32]);
+/* The same two on device-resident polynomials (no copies; d_out must not overlap d_coeffs). */
+int h2a_coeff_to_extended_dev(h2a_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k,
+                              const uint8_t coset_shift[32], void* d_out /* 2^ext_k * 32 */);
+int h2a_extended_to_coeff_dev(h2a_ctx* ctx, void* d_ext, uint32_t ext_k, const uint8_t coset_shift[32]);
 /* omega_k = ROOT_OF_UNITY^(2^(28-k)), Montgomery form (EvaluationDomain::get_omega). */
 int h2a_fr_root_of_unity(uint32_t k, uint8_t out[32]);
 

@@ -359,6 +359,26 @@ def test_coset_extension_matches_oracle(ctx, orc, k, ext_k):
     assert bytes(back[:32 << k]) == bytes(coeffs) and not back[32 << k:].any()
 
 
+def test_coset_extension_on_device_pointers(ctx, orc):
+    """h2a_coeff_to_extended_dev / h2a_extended_to_coeff_dev: same bytes as the host-buffer entry points, round trip."""
+    k, ext_k = 11, 13
+    n, m = 1 << k, 1 << ext_k
+    coeffs = orc.gen_scalars(77, n)
+    zeta = fr_bytes(7)
+    want = ctx.coeff_to_extended(coeffs, k, ext_k, zeta)
+    d_in, d_out = ctx.dev_alloc(32 * n), ctx.dev_alloc(32 * m)
+    ctx.h2d(d_in, coeffs)
+    ctx.coeff_to_extended_dev(d_in, k, ext_k, zeta, d_out)
+    assert bytes(ctx.d2h(d_out, 32 * m)) == bytes(want)
+    assert bytes(ctx.d2h(d_in, 32 * n)) == bytes(coeffs)          # the input is left alone
+    ctx.extended_to_coeff_dev(d_out, ext_k, zeta)
+    back = ctx.d2h(d_out, 32 * m)
+    assert bytes(back[:32 * n]) == bytes(coeffs) and bytes(back[32 * n:]) == bytes(32 * (m - n))
+    with pytest.raises(h2a.H2AError):
+        ctx.coeff_to_extended_dev(d_out, k, ext_k, zeta, d_out)       # overlapping buffers are refused
+    ctx.dev_free(d_in); ctx.dev_free(d_out)
+
+
 def test_ntt_roundtrip_and_linearity_at_bench_size(ctx, orc):
     k = 22
     n = 1 << k
