@@ -274,9 +274,16 @@ int h2a_ntt_dev(h2a_ctx* ctx, void* d_a, uint32_t log_n, const uint8_t omega[32]
     if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
     const size_t bytes = 32ull << log_n;
     H2A_TRY(h2a_reserve(ctx, ctx->ntt_b, bytes));
-    H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)d_a, 1u << log_n, (uint8_t*)d_a, (uint8_t*)ctx->ntt_b.p, log_n, omega, inverse,
-                        coset_shift));
-    H2A_CUDA(ctx, cudaMemcpyAsync(d_a, ctx->ntt_b.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (log_n >= 12) {
+        // at least two passes (a pass covers at most 2^10 points): the first reads d_a and writes the workspace, the
+        // last one writes the natural-order result back into d_a — no copy
+        H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)d_a, 1u << log_n, (uint8_t*)ctx->ntt_b.p, (uint8_t*)d_a, log_n, omega, inverse,
+                            coset_shift));
+    } else {
+        H2A_TRY(h2a_ntt_run(ctx, (const uint8_t*)d_a, 1u << log_n, (uint8_t*)d_a, (uint8_t*)ctx->ntt_b.p, log_n, omega, inverse,
+                            coset_shift));
+        H2A_CUDA(ctx, cudaMemcpyAsync(d_a, ctx->ntt_b.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2A_OK;
 }
