@@ -216,6 +216,9 @@ class Context:
     def set_msm_host_split(self, pieces):
         self._check(self.lib.h2a_msm_set_host_split(self.h, int(pieces)))
 
+    def set_msm_group(self, cols, cols_host=2):
+        self._check(self.lib.h2a_msm_set_group(self.h, int(cols), int(cols_host)))
+
     def msm(self, bases, scalars, offset=0):
         """best_multiexp over resident bases, host scalars.  Returns the 64-byte affine result."""
         scalars = _bytes(scalars)

@@ -98,6 +98,13 @@ int h2a_msm_set_host_split(h2a_ctx* ctx, int pieces) {
     return H2A_OK;
 }
 
+int h2a_msm_set_group(h2a_ctx* ctx, int cols, int cols_host) {
+    if (!ctx || cols < 1 || cols > 64 || cols_host < 1 || cols_host > 64) return H2A_ERR_INVALID;
+    ctx->msm_group_cols = cols;
+    ctx->msm_group_cols_host = cols_host;
+    return H2A_OK;
+}
+
 int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
                    uint8_t out_affine[64]) {
     if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;

@@ -25,6 +25,7 @@ struct h2a_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;       // second stream of this lane (the two halves of the affine tree)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int stream_priority = 0;              // priority both streams are created with (the device's greatest)
     std::string err;
     uint64_t launches = 0;
     int msm_window_override = 0;
@@ -33,6 +34,8 @@ struct h2a_ctx {
     int msm_red_chunk = 2048;  // segments per block at level 2 of the bucket reduction (power of two)
     int msm_seg_len = 16;  // buckets per thread at level 1 of the bucket reduction (power of two)
     int msm_host_split = 2;  // point ranges a large host-scalar MSM is cut into so copies overlap compute (1 = off)
+    int msm_group_cols = 8;       // columns one pass of a device-resident batch takes (tables only; 1 = one MSM per column)
+    int msm_group_cols_host = 2;  // the same when the columns are copied from host memory on the way
     int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
     // profiling
@@ -53,7 +56,8 @@ struct h2a_ctx {
         bool active = false;
         bool pre = false;
         int c = 0;
-        uint32_t groups = 0;
+        uint32_t groups = 0;   // points per column waiting in the pinned buffer
+        uint32_t cols = 1;     // columns of this pass (h2a_msm_launch_cols)
         uint32_t log_l = 0;  // log2 of the reduction's segment length (the host finishes the single-window Horner)
     } msm_pending;
     h2a_ctx* alt = nullptr;  // second lane (own stream + workspace) for pipelined batches; created on first use
@@ -118,7 +122,8 @@ int h2a_msm_precompute(h2a_ctx* ctx, h2a_bases* bases, int c);
 // the two halves of h2a_msm_run: queue every kernel and the copy of the window sums (no host synchronisation), then
 // wait and combine on the host.  One MSM may be pending per ctx (lane).
 int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n);
-int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]);
+int h2a_msm_launch_cols(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_cols, int m, size_t n);
+int h2a_msm_finish(h2a_ctx* ctx, uint8_t* out_affine /* 64 bytes per column of the pending pass */);
 // m MSMs over the same bases with device-resident scalars, pipelined over two lanes
 int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m, uint8_t* out_affine,
                       const uint8_t* const* h_src = nullptr);

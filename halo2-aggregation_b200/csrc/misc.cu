@@ -233,7 +233,12 @@ int h2a_init(h2a_ctx** out, int device) {
     h2a_ctx* ctx = new h2a_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the lanes that carry commitments run at the highest stream priority: work queued on a default-priority stream
+    // (the prover's transform lane, plonk_prove.cu) then only fills the SMs they leave idle
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    ctx->stream_priority = prio_greatest;
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, ctx->stream_priority) != cudaSuccess) {
         delete ctx;
         return H2A_ERR_CUDA;
     }
@@ -247,6 +252,10 @@ int h2a_init(h2a_ctx** out, int device) {
     if (env && atoi(env) >= 128 && atoi(env) <= 65536 && (atoi(env) & (atoi(env) - 1)) == 0) ctx->msm_red_chunk = atoi(env);
     env = getenv("H2A_MSM_HOST_SPLIT");
     if (env && atoi(env) >= 1 && atoi(env) <= 16) ctx->msm_host_split = atoi(env);
+    env = getenv("H2A_MSM_GROUP");
+    if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_group_cols = atoi(env);
+    env = getenv("H2A_MSM_GROUP_HOST");
+    if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_group_cols_host = atoi(env);
     env = getenv("H2A_MSM_ALGO");
     if (env) ctx->msm_algo = atoi(env) ? 1 : 0;
     *out = ctx;

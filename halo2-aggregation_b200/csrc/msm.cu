@@ -21,6 +21,7 @@
 // a dense contraction, so no tensor cores.
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "ctx.hpp"
 #include "curve.cuh"
@@ -608,12 +609,18 @@ int pick_window(size_t n) {  // from the measured sweep (tools/sweep.py --window
     return std::max(6, std::min(10, lg - 4));
 }
 
+// M columns of n scalars each over the same bases in ONE pass (PRE only for M > 1): column j owns the bucket set
+// [j * B, (j + 1) * B) exactly as window w does without tables, so the scan, the tree, the task kernels and the bucket
+// reduction see one MSM of M * n points — the launch-bound and latency-bound phases are paid once per group of columns
+// instead of once per column — and the reduction leaves one result (nbits + 1 level sums) per column.
 template <int C, bool PRE>
-int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t first, const uint8_t* d_scalars, size_t n) {
+int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t first, const uint8_t* const* d_cols, int M, size_t n_col) {
     constexpr int W = Win<C>::W;
     constexpr uint32_t B = Win<C>::B;
-    constexpr int BW = PRE ? 1 : W;  // windows of buckets
+    if (M < 1 || (!PRE && M != 1)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: %d columns in one pass need precomputed tables", M);
+    const int BW = PRE ? M : W;  // sets of buckets: one per column (tables) or one per window
     const uint32_t nb = (uint32_t)BW * B;
+    const size_t n = n_col * (size_t)M;   // points of the whole pass
     if ((uint64_t)n * W >= (1ull << 32) || (PRE && (uint64_t)stride * W >= (1ull << 31)))
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu with %d windows overflows 32-bit positions", n, W);
     // bucket reduction geometry (see msm_reduce_l1_kernel): segments of 2^log_l buckets, chunks of <= 2048 segments
@@ -624,7 +631,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     while ((1u << nbits) < segs) nbits++;
     const uint32_t chunk_len = std::min(segs, (uint32_t)ctx->msm_red_chunk), chunks = segs / chunk_len;
     // points returned to the host: one per window, or (PRE) the nbits + 1 level sums of the single window
-    const uint32_t groups = PRE ? nbits + 1u : (uint32_t)W;
+    const uint32_t groups = PRE ? (nbits + 1u) * (uint32_t)M : (uint32_t)W;
     const uint32_t scan_blocks = (nb + SCAN_CHUNK - 1) / SCAN_CHUNK;
     // task length: twice the mean bucket load (uniformly distributed digits then give one task per bucket while
     // the fuller buckets fed by a narrow top window are cut into a few equal tasks), shorter when buckets are scarce
@@ -671,9 +678,11 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     h2a_prof_begin(ctx, 0);
     H2A_CUDA(ctx, cudaMemsetAsync(offsets, 0, (size_t)nb * 4, st));
     H2A_CUDA(ctx, cudaMemsetAsync(n_multi, 0, 8, st));
-    const uint32_t pt_blocks = (uint32_t)((n + 255) / 256);
-    msm_hist_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, offsets);
-    H2A_LAUNCH_CHECK(ctx);
+    const uint32_t pt_blocks = (uint32_t)((n_col + 255) / 256);
+    for (int col = 0; col < M; col++) {
+        msm_hist_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_cols[col], (uint32_t)n_col, offsets + (size_t)col * B);
+        H2A_LAUNCH_CHECK(ctx);
+    }
     h2a_prof_mark(ctx);
     scan_block_sums_kernel<<<scan_blocks, SCAN_THREADS, 0, st>>>(offsets, nb, task_len, pad, block_sums);
     H2A_LAUNCH_CHECK(ctx);
@@ -690,8 +699,10 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
         H2A_CUDA(ctx, cudaMemcpyAsync(starts, offsets, (size_t)nb * 4, cudaMemcpyDeviceToDevice, st));
         H2A_CUDA(ctx, cudaMemsetAsync(sorted, 0xff, (size_t)total_padded * 4, st));
     }
-    msm_scatter_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_scalars, (uint32_t)n, stride, first, offsets, sorted);
-    H2A_LAUNCH_CHECK(ctx);
+    for (int col = 0; col < M; col++) {
+        msm_scatter_kernel<C, PRE><<<pt_blocks, 256, 0, st>>>(d_cols[col], (uint32_t)n_col, stride, first, offsets + (size_t)col * B, sorted);
+        H2A_LAUNCH_CHECK(ctx);
+    }
     h2a_prof_mark(ctx);
     if (R == 0) {
         msm_accumulate_kernel<<<(max_tasks + 127) / 128, 128, 0, st>>>(d_bases, sorted, offsets, task_off, nb, task_len, !PRE,
@@ -702,7 +713,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
         H2A_TRY(h2a_reserve(ctx, ctx->aff_b, (size_t)(total_padded / 4 + 1) * 64));
         // the two halves of the slot array are independent trees: they run on two streams so that one half's
         // forward / backward kernels fill the latency gap of the other half's totals inversion
-        if (!ctx->stream2) H2A_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+        if (!ctx->stream2) H2A_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, ctx->stream_priority));
         if (!ctx->ev_fork) {
             H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
             H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
@@ -802,28 +813,31 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     ctx->msm_pending.active = true;
     ctx->msm_pending.pre = PRE;
     ctx->msm_pending.c = C;
-    ctx->msm_pending.groups = groups;
+    ctx->msm_pending.groups = PRE ? nbits + 1u : groups;
+    ctx->msm_pending.cols = PRE ? (uint32_t)M : 1u;
     ctx->msm_pending.log_l = log_l;
     return H2A_OK;
 }
 
 }  // namespace
 
-int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n) {
+namespace {
+int msm_dispatch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* const* d_cols, int m, size_t n) {
     if (ctx->msm_pending.active) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: a launch is already pending on this lane");
     if (n == 0) {
         ctx->msm_pending.active = true;
         ctx->msm_pending.groups = 0;
+        ctx->msm_pending.cols = (uint32_t)m;
         return H2A_OK;
     }
-    if (n > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n);
+    if (n * (size_t)m > ((size_t)1 << 27)) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: n=%zu exceeds 2^27 points per call", n * (size_t)m);
     const bool pre = bases->table != nullptr && (ctx->msm_window_override == 0 || ctx->msm_window_override == bases->table_c);
     int c = pre ? bases->table_c : (ctx->msm_window_override ? ctx->msm_window_override : pick_window(n));
     switch (c) {
-#define H2A_CASE(C)                                                                                              \
-    case C:                                                                                                      \
-        return pre ? msm_launch_c<C, true>(ctx, bases->table, (uint32_t)bases->n, (uint32_t)offset, d_scalars, n) \
-                   : msm_launch_c<C, false>(ctx, bases->d + 64 * offset, 0, 0, d_scalars, n);
+#define H2A_CASE(C)                                                                                                 \
+    case C:                                                                                                         \
+        return pre ? msm_launch_c<C, true>(ctx, bases->table, (uint32_t)bases->n, (uint32_t)offset, d_cols, m, n)   \
+                   : msm_launch_c<C, false>(ctx, bases->d + 64 * offset, 0, 0, d_cols, m, n);
         H2A_CASE(6) H2A_CASE(7) H2A_CASE(8) H2A_CASE(9) H2A_CASE(10) H2A_CASE(11) H2A_CASE(12) H2A_CASE(13)
         H2A_CASE(14) H2A_CASE(15) H2A_CASE(16) H2A_CASE(17) H2A_CASE(18) H2A_CASE(19) H2A_CASE(20)
 #undef H2A_CASE
@@ -831,30 +845,45 @@ int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const ui
             H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: window width %d not in 6..20", c);
     }
 }
+}  // namespace
 
-int h2a_msm_finish(h2a_ctx* ctx, uint8_t out_affine[64]) {
+int h2a_msm_launch(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* d_scalars, size_t n) {
+    return msm_dispatch(ctx, bases, offset, &d_scalars, 1, n);
+}
+// m columns of n scalars each over bases [0, n) in one pass; needs the precomputed tables.  h2a_msm_finish then writes m points.
+int h2a_msm_launch_cols(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_cols, int m, size_t n) {
+    if (m < 1) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: no columns");
+    return msm_dispatch(ctx, bases, 0, d_cols, m, n);
+}
+
+int h2a_msm_finish(h2a_ctx* ctx, uint8_t* out_affine) {
     if (!ctx->msm_pending.active) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: nothing pending on this lane");
     ctx->msm_pending.active = false;
+    const uint32_t cols = std::max(1u, ctx->msm_pending.cols);
     if (ctx->msm_pending.groups == 0) {
-        memset(out_affine, 0, 64);
+        memset(out_affine, 0, 64 * (size_t)cols);
         return H2A_OK;
     }
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     using namespace h2a_host;
     const uint8_t* ws = (const uint8_t*)ctx->pinned;
-    PointX acc = px_identity();
-    if (ctx->msm_pending.pre) {  // single window (the tables carry the 2^(c*w) factors): T + 2^log_l * sum_b 2^b P_b
+    if (ctx->msm_pending.pre) {  // per column a single window (the tables carry the 2^(c*w) factors): T + 2^log_l * sum_b 2^b P_b
         const uint32_t nbits = ctx->msm_pending.groups - 1;
-        for (int b = (int)nbits - 1; b >= 0; b--) acc = px_add(px_dbl(acc), px_load(ws + 128 * b));
-        for (uint32_t i = 0; i < ctx->msm_pending.log_l; i++) acc = px_dbl(acc);
-        acc = px_add(acc, px_load(ws + 128 * nbits));
+        for (uint32_t col = 0; col < cols; col++, ws += 128 * (size_t)(nbits + 1)) {
+            PointX acc = px_identity();
+            for (int b = (int)nbits - 1; b >= 0; b--) acc = px_add(px_dbl(acc), px_load(ws + 128 * b));
+            for (uint32_t i = 0; i < ctx->msm_pending.log_l; i++) acc = px_dbl(acc);
+            acc = px_add(acc, px_load(ws + 128 * nbits));
+            affine_store(out_affine + 64 * (size_t)col, px_to_affine(acc));
+        }
     } else {                     // Horner over the window sums: acc = acc * 2^c + S_w, top window first
+        PointX acc = px_identity();
         for (int w = (int)ctx->msm_pending.groups - 1; w >= 0; w--) {
             for (int i = 0; i < ctx->msm_pending.c; i++) acc = px_dbl(acc);
             acc = px_add(acc, px_load(ws + 128 * w));
         }
+        affine_store(out_affine, px_to_affine(acc));
     }
-    affine_store(out_affine, px_to_affine(acc));
     h2a_prof_mark(ctx);
     h2a_prof_end(ctx);
     return H2A_OK;
@@ -869,8 +898,11 @@ int h2a_msm_run(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8
 // Two lanes alternate: while lane A's latency-bound tail (bucket reduction, window sums, copy back) drains, lane B's
 // histogram / scatter / accumulation kernels already occupy the SMs.  Lane B first waits for everything queued on the
 // main stream, so scalars produced there by earlier kernels are complete.
+// With precomputed tables and columns of equal length, a lane takes a GROUP of columns per pass (msm_launch_c with
+// M > 1, at most ctx->msm_group_cols of them and 2^23 points): the whole group shares one scan, one tree and one
+// bucket reduction.
 // h_src (optional): column j is first copied from host memory h_src[j] into d_scalars[j] on its lane's stream, so the
-// copy of one column overlaps the computation of the previous one.
+// copy of one pass overlaps the computation of the previous one (groups stay small there: the first pass's copies are exposed).
 int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m,
                       uint8_t* out_affine, const uint8_t* const* h_src) {
     if (m <= 0) return H2A_OK;
@@ -883,33 +915,51 @@ int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const
     H2A_TRY(h2a_get_alt(ctx, &alt));
     alt->msm_window_override = ctx->msm_window_override;
     alt->msm_algo = ctx->msm_algo;
+    // pass sizes
+    bool same_n = n[0] > 0;
+    for (int j = 1; j < m; j++) same_n = same_n && n[j] == n[0];
+    const bool pre = bases->table != nullptr && (ctx->msm_window_override == 0 || ctx->msm_window_override == bases->table_c);
+    int gmax = 1;
+    if (pre && same_n && ctx->msm_algo == 1) {
+        gmax = h_src ? ctx->msm_group_cols_host : ctx->msm_group_cols;
+        while (gmax > 1 && n[0] * (size_t)gmax > ((size_t)1 << 23)) gmax--;
+    }
+    int passes = (m + gmax - 1) / gmax;
+    if (passes == 1 && m >= 4) passes = 2;   // both lanes get work
+    std::vector<int> first(passes + 1, 0);
+    for (int q = 0; q < passes; q++) first[q + 1] = first[q] + m / passes + (q < m % passes ? 1 : 0);
+
     cudaEvent_t ready;
     H2A_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     H2A_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
     H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, ready, 0));
     h2a_ctx* lanes[2] = {ctx, alt};
-    int pending_col[2] = {-1, -1};
+    int pending_pass[2] = {-1, -1};
     int rc = H2A_OK;
     const bool prof = ctx->profiling;
     ctx->profiling = false;  // per-phase events of interleaved launches would be meaningless
-    for (int j = 0; j < m && rc == H2A_OK; j++) {
-        h2a_ctx* lane = lanes[j & 1];
-        if (pending_col[j & 1] >= 0) {
-            rc = h2a_msm_finish(lane, out_affine + 64 * pending_col[j & 1]);
-            pending_col[j & 1] = -1;
+    for (int q = 0; q < passes && rc == H2A_OK; q++) {
+        h2a_ctx* lane = lanes[q & 1];
+        if (pending_pass[q & 1] >= 0) {
+            rc = h2a_msm_finish(lane, out_affine + 64 * (size_t)first[pending_pass[q & 1]]);
+            pending_pass[q & 1] = -1;
             if (rc != H2A_OK) break;
         }
-        if (h_src && h_src[j] && n[j]) {
-            cudaError_t e = cudaMemcpyAsync((void*)d_scalars[j], h_src[j], 32 * n[j], cudaMemcpyHostToDevice, lane->stream);
-            if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = H2A_ERR_CUDA; break; }
-        }
-        rc = h2a_msm_launch(lane, bases, 0, d_scalars[j], n[j]);
-        if (rc == H2A_OK) pending_col[j & 1] = j;
+        const int j0 = first[q], cnt = first[q + 1] - j0;
+        if (h_src)
+            for (int j = j0; j < j0 + cnt; j++) {
+                if (!h_src[j] || !n[j]) continue;
+                cudaError_t e = cudaMemcpyAsync((void*)d_scalars[j], h_src[j], 32 * n[j], cudaMemcpyHostToDevice, lane->stream);
+                if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = H2A_ERR_CUDA; break; }
+            }
+        if (rc != H2A_OK) break;
+        rc = cnt == 1 ? h2a_msm_launch(lane, bases, 0, d_scalars[j0], n[j0]) : h2a_msm_launch_cols(lane, bases, d_scalars + j0, cnt, n[j0]);
+        if (rc == H2A_OK) pending_pass[q & 1] = q;
         else if (lane != ctx) ctx->err = lane->err;
     }
     for (int l = 0; l < 2; l++) {
-        if (pending_col[l] >= 0) {
-            int r2 = h2a_msm_finish(lanes[l], out_affine + 64 * pending_col[l]);
+        if (pending_pass[l] >= 0) {
+            int r2 = h2a_msm_finish(lanes[l], out_affine + 64 * (size_t)first[pending_pass[l]]);
             if (rc == H2A_OK) rc = r2;
         }
     }

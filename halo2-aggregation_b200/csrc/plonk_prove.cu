@@ -624,11 +624,20 @@ struct ProverState {
     EvalTables tab_n;
     QuotientArgs qargs;
     std::vector<float> phase_ms;
+    // transform lane: the lagrange -> coefficient -> extended-coset transforms of a committed column are queued here as
+    // soon as the column is final, so they run under the commitments (and the lookup sorts) of the main lanes instead of
+    // in a phase of their own.  Default priority, i.e. below the ctx streams (misc.cu): it takes the SMs the MSM leaves idle.
+    cudaStream_t ntt_stream = nullptr;
+    cudaEvent_t ev_cols_ready = nullptr, ev_ntt_done = nullptr;
+    bool overlap_ntt = true;
 };
 
 void h2a_prover_state_free(h2a_ctx* ctx, ProverState* p) {
     if (!p) return;
     cudaStreamSynchronize(ctx->stream);
+    if (p->ntt_stream) { cudaStreamSynchronize(p->ntt_stream); cudaStreamDestroy(p->ntt_stream); }
+    if (p->ev_cols_ready) cudaEventDestroy(p->ev_cols_ready);
+    if (p->ev_ntt_done) cudaEventDestroy(p->ev_ntt_done);
     if (p->arena) cudaFree(p->arena);
     if (p->xtab.p) cudaFree(p->xtab.p);
     delete p;
@@ -680,6 +689,35 @@ int to_ext(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* coef, uint8_t* ext) {
     hh::fr_store(w, hh::fr_root_of_unity((int)c->shape.ext_k));
     return h2a_ntt_run(ctx, coef, c->shape.n, c->prover->tmp_m, ext, c->shape.ext_k, w, 0, c->prover->coset);
 }
+// to_coef + to_ext of a group of columns on the transform lane, ordered after everything queued on the ctx stream so far
+// (the columns' last writes).  tmp_n[3] / tmp_m are the lane's work buffers: nothing else touches them during a proof.
+// Without the lane (H2A_PROVE_NTT_OVERLAP=0) the same transforms are queued on the ctx stream itself.
+int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& cols) {
+    ProverState* p = c->prover;
+    if (cols.empty()) return H2A_OK;
+    if (!p->overlap_ntt) {
+        for (Poly3* q : cols) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
+        return H2A_OK;
+    }
+    H2A_CUDA(ctx, cudaEventRecord(p->ev_cols_ready, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamWaitEvent(p->ntt_stream, p->ev_cols_ready, 0));
+    struct Swap {   // h2a_ntt_run launches on ctx->stream
+        h2a_ctx* c; cudaStream_t saved;
+        Swap(h2a_ctx* c_, cudaStream_t s_) : c(c_), saved(c_->stream) { c->stream = s_; }
+        ~Swap() { c->stream = saved; }
+    } swap(ctx, p->ntt_stream);
+    for (Poly3* q : cols) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
+    return H2A_OK;
+}
+// the ctx stream waits for everything queued on the transform lane
+int join_transforms(h2a_ctx* ctx, h2a_circuit* c) {
+    ProverState* p = c->prover;
+    if (!p->overlap_ntt) return H2A_OK;
+    H2A_CUDA(ctx, cudaEventRecord(p->ev_ntt_done, p->ntt_stream));
+    H2A_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, p->ev_ntt_done, 0));
+    return H2A_OK;
+}
+
 int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint32_t n, hh::PointA& out) {
     uint8_t b[64];
     H2A_TRY(h2a_msm_run(ctx, bases, 0, d_scalars, n, b));
@@ -816,6 +854,12 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     p->g = g;
     p->g_lagrange = g_lagrange;
     memcpy(p->coset, coset_shift, 32);
+    if (const char* env = getenv("H2A_PROVE_NTT_OVERLAP")) p->overlap_ntt = atoi(env) != 0;
+    if (p->overlap_ntt) {
+        H2A_CUDA(ctx, cudaStreamCreateWithFlags(&p->ntt_stream, cudaStreamNonBlocking));
+        H2A_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_cols_ready, cudaEventDisableTiming));
+        H2A_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_ntt_done, cudaEventDisableTiming));
+    }
 
     // programs: gates first, then per lookup its inputs then its tables
     std::vector<uint32_t> code;
@@ -1048,6 +1092,12 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         }
         for (uint32_t i = 0; i < s.n_advice; i++) write_point(cms[s.n_instance + i]);
     }
+    {   // the columns are resident now: their transforms run under the lookup permutations below
+        std::vector<Poly3*> cols;
+        for (auto& q : p->advice) cols.push_back(&q);
+        for (auto& q : p->instance) cols.push_back(&q);
+        H2A_TRY(transform_columns(ctx, c, cols));
+    }
     steps.mark("instance+advice commitments");
     hh::Fr theta = tr.squeeze();                                                   // :378
     H2A_TRY(upload_fr(ctx, slot(S_THETA), theta));
@@ -1084,6 +1134,11 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         bl += 32ull * bf;  // this lookup's Z tail, consumed after beta and gamma
     }
     if (!s.lookups.empty()) {
+        {
+            std::vector<Poly3*> tcols;
+            for (auto& l : p->lk) { tcols.push_back(&l.pa); tcols.push_back(&l.ps); }
+            H2A_TRY(transform_columns(ctx, c, tcols));
+        }
         std::vector<const uint8_t*> cols;
         for (auto& l : p->lk) { cols.push_back(l.pa.lag); cols.push_back(l.ps.lag); }
         std::vector<hh::PointA> cms;
@@ -1144,6 +1199,12 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         LAUNCH1D(dev::shift_scale_kernel, n, 256, p->tmp_n[2], slot(S_Z0), n, l.z.lag);
         H2A_CUDA(ctx, cudaMemcpyAsync(l.z.lag + 32ull * (n - bf), bl_lookup_z[li], 32ull * bf, cudaMemcpyHostToDevice, st));
     }
+    {
+        std::vector<Poly3*> tcols;
+        for (auto& q : p->pz) tcols.push_back(&q);
+        for (auto& l : p->lk) tcols.push_back(&l.z);
+        H2A_TRY(transform_columns(ctx, c, tcols));
+    }
     {   // permutation Z (:402-409) then lookup Z (:411-417) commitments, one batch
         std::vector<const uint8_t*> cols;
         for (auto& q : p->pz) cols.push_back(q.lag);
@@ -1161,12 +1222,9 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     }
     hh::Fr y = tr.squeeze();                                                       // :423
 
-    // coefficient and extended forms of everything the quotient touches
-    for (auto& q : p->advice) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
-    for (auto& q : p->instance) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
-    for (auto& q : p->pz) { H2A_TRY(to_coef(ctx, c, q.lag, q.coef)); H2A_TRY(to_ext(ctx, c, q.coef, q.ext)); }
-    for (auto& l : p->lk)
-        for (Poly3* q : {&l.pa, &l.ps, &l.z}) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
+    // coefficient and extended forms of everything the quotient touches: queued on the transform lane as each group of
+    // columns became final (transform_columns above); this phase is what is left of them when the commitments are done
+    H2A_TRY(join_transforms(ctx, c));
     steps.mark("ifft + coset fft of committed columns");
     hh::fr_store(p->qargs.beta, beta); hh::fr_store(p->qargs.gamma, gamma); hh::fr_store(p->qargs.theta, theta); hh::fr_store(p->qargs.y, y);
     H2A_CUDA(ctx, cudaMemcpyAsync(p->d_qargs, &p->qargs, sizeof(QuotientArgs), cudaMemcpyHostToDevice, st));

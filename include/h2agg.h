@@ -98,6 +98,11 @@ int h2a_msm_set_algorithm(h2a_ctx* ctx, int algo);
 /* h2a_msm_g1 with >= 2^21 host scalars is cut into `pieces` point ranges so that the scalar copy of one range
  * overlaps the computation of the previous one (default 2; 1 = one copy then one MSM).  Same result bit for bit. */
 int h2a_msm_set_host_split(h2a_ctx* ctx, int pieces);
+/* h2a_msm_g1_batch_dev over bases with precomputed tables and columns of equal length commits up to `cols` columns
+ * in ONE pass (one scan, one addition tree and one bucket reduction for the whole group; default 8, 1 = one MSM per
+ * column); `cols_host` is the same limit inside the prover when the columns are copied from host memory on the way
+ * (default 2).  Same results bit for bit. */
+int h2a_msm_set_group(h2a_ctx* ctx, int cols, int cols_host);
 
 /* ---- Fr NTT ------------------------------------------------------------------------------
  * Replaces halo2 `arithmetic::best_fft(a, omega, log_n)` and the `EvaluationDomain` methods

@@ -269,6 +269,45 @@ def test_msm_pipelined_batches(ctx, orc):
     hb.free()
 
 
+@pytest.mark.parametrize("c,group", [(16, 8), (12, 3), (16, 64)])
+def test_msm_grouped_columns(ctx, orc, c, group):
+    """Columns of equal length over bases with tables are committed several per pass (one bucket set per column):
+    every column still gets its own best_multiexp value, whatever its scalars look like and however the batch is cut."""
+    n = 1 << 13
+    r_minus_1 = (0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001 - 1).to_bytes(32, "little")
+    raw = lambda b: orc.to_mont(1, np.frombuffer(b * n, dtype=np.uint8))
+    small = np.zeros((n, 32), np.uint8)
+    small[:, :2] = np.random.default_rng(5).integers(0, 256, size=(n, 2), dtype=np.uint8)
+    sel = np.zeros((n, 32), np.uint8)
+    sel[::3, 0] = 1
+    cols = [orc.gen_scalars(300, n), np.zeros(32 * n, np.uint8), raw((1).to_bytes(32, "little")), raw(r_minus_1),
+            orc.to_mont(1, small.reshape(-1)), orc.to_mont(1, sel.reshape(-1)), orc.gen_scalars(301, n), orc.gen_scalars(302, n),
+            orc.gen_scalars(303, n)]
+    bases = orc.gen_bases(310, n)
+    bases[64 * 5:64 * 6] = 0                              # an identity among the bases
+    bases[64 * 8:64 * 9] = bases[64 * 7:64 * 8]           # a repeated base (P + P inside a bucket)
+    want = [bytes(orc.msm(bases, col)) for col in cols]
+    hb = ctx.upload_bases(bases).precompute(c)
+    dptrs = []
+    for col in cols:
+        d = ctx.dev_alloc(col.size); ctx.h2d(d, col); dptrs.append(d)
+    ctx.set_msm_group(group, 2)
+    try:
+        for m in (len(cols), 4, 2):
+            got = ctx.msm_batch_dev(hb, dptrs[:m], [n] * m)
+            assert [bytes(g) for g in got] == want[:m]
+        # a single call afterwards (no pending state left behind), and the ungrouped path
+        assert bytes(ctx.msm_dev(hb, dptrs[0], n)) == want[0]
+        ctx.set_msm_group(1, 1)
+        got = ctx.msm_batch_dev(hb, dptrs, [n] * len(cols))
+        assert [bytes(g) for g in got] == want
+    finally:
+        ctx.set_msm_group(8, 2)
+        for d in dptrs:
+            ctx.dev_free(d)
+        hb.free()
+
+
 def test_msm_linearity_at_bench_size(ctx):
     """2^22 points (BASELINE metric size): MSM(s, B) over [0,n) equals the sum of MSMs over two halves,
     and MSM with all-one scalars over the first 2^16 bases equals the plain point sum."""

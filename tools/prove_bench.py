@@ -190,7 +190,8 @@ def main():
         res["proofs_identical_across_ranks"] = all(bool((d == alld[0]).all()) for d in alld)
         res["config"]["distribution"] = "commitments column-parallel over %d GPUs (64-byte results allgathered with NCCL); everything else replicated" % args.world
     else:
-        res.pop("proof_digest_src", None)
+        import hashlib
+        res["proof_sha256"] = hashlib.sha256(res.pop("proof_digest_src")).hexdigest()
     if args.rank == 0:
         print(json.dumps(res), flush=True)
     if args.world > 1:
