@@ -36,6 +36,7 @@ struct h2a_ctx {
     int msm_host_split = 2;  // point ranges a large host-scalar MSM is cut into so copies overlap compute (1 = off)
     int msm_group_cols = 8;       // columns one pass of a device-resident batch takes (tables only; 1 = one MSM per column)
     int msm_group_cols_host = 2;  // the same when the columns are copied from host memory on the way
+    int msm_rounds_bias = 0;      // experiment knob (H2A_MSM_ROUNDS_BIAS): added to the number of regular tree rounds
     int msm_algo = 1;  // 0: XYZZ mixed additions, one thread per bucket task; 1: pairwise tree of batched affine additions
 
     // profiling

@@ -256,6 +256,8 @@ int h2a_init(h2a_ctx** out, int device) {
     if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_group_cols = atoi(env);
     env = getenv("H2A_MSM_GROUP_HOST");
     if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_group_cols_host = atoi(env);
+    env = getenv("H2A_MSM_ROUNDS_BIAS");
+    if (env && atoi(env) >= -3 && atoi(env) <= 3) ctx->msm_rounds_bias = atoi(env);
     env = getenv("H2A_MSM_ALGO");
     if (env) ctx->msm_algo = atoi(env) ? 1 : 0;
     *out = ctx;

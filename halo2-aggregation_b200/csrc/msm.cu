@@ -43,6 +43,7 @@ struct Win {
 
 // Signed-digit recoding of a canonical 254-bit scalar: digit_w in (-2^(c-1), 2^(c-1)], carries
 // ripple upward; the top window never overflows because 254 - (W-1)c <= c-1 for every c in 3..24.
+// f(w, mag, neg) is called for EVERY window (mag == 0: no entry), so a warp stays converged across the calls.
 template <int C, class F>
 __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], F f) {
     constexpr int W = Win<C>::W;
@@ -58,8 +59,20 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], F f) {
         const bool neg = v > B;
         carry = neg ? 1u : 0u;
         const uint32_t mag = neg ? (2u * B - v) : v;
-        if (mag) f(w, mag - 1u, neg);
+        f(w, mag, neg);
     }
+}
+
+// Do the lowest digits of this warp's scalars collide?  Uniformly random scalars never do (32 draws from 2^(c-1)
+// buckets); small, repeated or sorted ones — selector and range-checked columns, permuted lookup columns, grand
+// products that stay at one — always do, and their plain atomics then serialise on a handful of counters.  Such a
+// warp issues ONE atomic per distinct bucket (match.any groups the lanes) instead of one per lane.
+template <int C>
+__device__ __forceinline__ bool warp_digits_collide(const uint32_t (&s)[8], bool live) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t key = live ? (s[0] & ((1u << (C < 32 ? C : 31)) - 1u)) : (0x80000000u | lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    return __any_sync(0xffffffffu, (peers & (peers - 1u)) != 0u);
 }
 
 // PRE = the bases carry precomputed window tables T[w][i] = 2^(c*w) * P_i: every window then feeds the
@@ -67,10 +80,20 @@ __device__ __forceinline__ void for_each_digit(const uint32_t (&s)[8], F f) {
 template <int C, bool PRE>
 __global__ void __launch_bounds__(256) msm_hist_kernel(const uint8_t* __restrict__ scalars, uint32_t n,
                                                        uint32_t* __restrict__ hist) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = Fr::load(scalars + 32ull * i).from_mont();
-    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool) { atomicAdd(&hist[PRE ? b : (uint32_t)w * Win<C>::B + b], 1u); });
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const bool live = i < n;     // the grid is whole warps; dead lanes stay for the warp votes
+    Fr s = live ? Fr::load(scalars + 32ull * i).from_mont() : Fr::zero();
+    if (!warp_digits_collide<C>(s.l, live)) {
+        for_each_digit<C>(s.l, [&](int w, uint32_t mag, bool) {
+            if (mag) atomicAdd(&hist[(PRE ? 0u : (uint32_t)w * Win<C>::B) + mag - 1u], 1u);
+        });
+        return;
+    }
+    for_each_digit<C>(s.l, [&](int w, uint32_t mag, bool) {
+        const uint32_t b = (PRE ? 0u : (uint32_t)w * Win<C>::B) + mag - 1u;
+        const unsigned peers = __match_any_sync(0xffffffffu, mag ? b : (0x80000000u | lane));
+        if (mag && lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(&hist[b], (uint32_t)__popc(peers));
+    });
 }
 
 template <int C, bool PRE>
@@ -78,13 +101,29 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint8_t* __restr
                                                           uint32_t stride, uint32_t first,
                                                           uint32_t* __restrict__ cursor,
                                                           uint32_t* __restrict__ sorted) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fr s = Fr::load(scalars + 32ull * i).from_mont();
-    for_each_digit<C>(s.l, [&](int w, uint32_t b, bool neg) {
-        uint32_t pos = atomicAdd(&cursor[PRE ? b : (uint32_t)w * Win<C>::B + b], 1u);
-        uint32_t idx = PRE ? (uint32_t)w * stride + first + i : i;
-        sorted[pos] = idx | (neg ? 0x80000000u : 0u);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const bool live = i < n;
+    Fr s = live ? Fr::load(scalars + 32ull * i).from_mont() : Fr::zero();
+    if (!warp_digits_collide<C>(s.l, live)) {
+        for_each_digit<C>(s.l, [&](int w, uint32_t mag, bool neg) {
+            if (!mag) return;
+            const uint32_t pos = atomicAdd(&cursor[(PRE ? 0u : (uint32_t)w * Win<C>::B) + mag - 1u], 1u);
+            const uint32_t idx = PRE ? (uint32_t)w * stride + first + i : i;
+            sorted[pos] = idx | (neg ? 0x80000000u : 0u);
+        });
+        return;
+    }
+    for_each_digit<C>(s.l, [&](int w, uint32_t mag, bool neg) {
+        const uint32_t b = (PRE ? 0u : (uint32_t)w * Win<C>::B) + mag - 1u;
+        const unsigned peers = __match_any_sync(0xffffffffu, mag ? b : (0x80000000u | lane));
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        uint32_t base = 0;
+        if (mag && lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (mag) {
+            const uint32_t idx = PRE ? (uint32_t)w * stride + first + i : i;
+            sorted[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = idx | (neg ? 0x80000000u : 0u);
+        }
     });
 }
 
@@ -666,6 +705,7 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
     int R = 0;
     if (ctx->msm_algo == 1) {
         while (R < 5 && (mean_load >> (R + 3)) >= 1) R++;   // keep >= 8 real points per 2^R of padding
+        if (ctx->msm_rounds_bias) R = std::max(0, std::min(5, R + ctx->msm_rounds_bias));
     }
     const uint32_t pad = 1u << R;
     const uint64_t padded_ub = (uint64_t)n * W + (uint64_t)(pad - 1) * std::min<uint64_t>(nb, (uint64_t)n * W);

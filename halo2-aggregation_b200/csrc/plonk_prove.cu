@@ -448,9 +448,13 @@ __global__ void key_stats_kernel(const uint8_t* keys, uint32_t u, uint32_t* stat
         atomicMax(&stats[1], lo);
     }
 }
+// lookup inputs repeat (that is what a lookup is for): one atomic per distinct key of a warp, not one per lane
 __global__ void count_keys_kernel(const uint8_t* keys, uint32_t u, uint32_t* hist) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < u) atomicAdd(&hist[ld(keys, i).l[0]], 1u);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31u;
+    const bool live = i < u;
+    const uint32_t key = live ? ld(keys, i).l[0] : (0x80000000u | lane);   // keys are < 2^COUNT_BITS
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (live && lane == (uint32_t)__ffs(peers) - 1u) atomicAdd(&hist[key], (uint32_t)__popc(peers));
 }
 // out[p] = the key whose run covers position p (offsets = exclusive prefix of the counters), sentinel beyond u
 __global__ void expand_counts_kernel(const uint32_t* offsets, uint32_t bins, uint32_t u, uint32_t n, uint8_t* out) {
@@ -856,7 +860,8 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     memcpy(p->coset, coset_shift, 32);
     if (const char* env = getenv("H2A_PROVE_NTT_OVERLAP")) p->overlap_ntt = atoi(env) != 0;
     if (p->overlap_ntt) {
-        H2A_CUDA(ctx, cudaStreamCreateWithFlags(&p->ntt_stream, cudaStreamNonBlocking));
+        const char* prio = getenv("H2A_PROVE_NTT_PRIO");   // experiment knob: 1 = same priority as the commitment lanes
+        H2A_CUDA(ctx, cudaStreamCreateWithPriority(&p->ntt_stream, cudaStreamNonBlocking, prio && atoi(prio) ? ctx->stream_priority : 0));
         H2A_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_cols_ready, cudaEventDisableTiming));
         H2A_CUDA(ctx, cudaEventCreateWithFlags(&p->ev_ntt_done, cudaEventDisableTiming));
     }
