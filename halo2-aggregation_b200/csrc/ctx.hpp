@@ -48,7 +48,7 @@ struct h2a_ctx {
     std::vector<const char*> prove_phase_names;
 
     // MSM workspace
-    DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc, aff_a, aff_b, aff_scratch, aff_u32;
+    DevBuf scalars, offsets, cursor, sorted, buckets, segsums, winsums, heavy, misc, aff_a, aff_b, aff_c, aff_scratch, aff_u32;
     void* pinned = nullptr;  // small pinned staging area for results
     size_t pinned_cap = 0;
 

@@ -20,6 +20,7 @@
 // The arithmetic is 254-bit Montgomery on the 32-bit integer pipe (field.cuh); nothing here is
 // a dense contraction, so no tensor cores.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -749,8 +750,16 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                                                                        partial);
         H2A_LAUNCH_CHECK(ctx);
     } else {
+        const uint32_t half_out0 = total_padded / 4;                                // outputs of round 0 per half
+        const uint32_t n_final = half_out0 >> (R - 1);                             // outputs of the last round per half
+        // Point arrays.  The halves run on two streams with nothing ordering one against the other, so they share no
+        // region: half h ping-pongs between its own part of aff_a (half_out0 points) and of aff_b (half_out0 / 2), and
+        // only the LAST round writes to the common array aff_c, half 0 in front of half 1, which nobody reads before
+        // the join.  (One shared ping-pong pair is a race: a half that gets a round ahead overwrites, with its round
+        // r+1 sums, points the other half is still reading in round r.)
         H2A_TRY(h2a_reserve(ctx, ctx->aff_a, (size_t)(total_padded / 2) * 64));
-        H2A_TRY(h2a_reserve(ctx, ctx->aff_b, (size_t)(total_padded / 4 + 1) * 64));
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_b, (size_t)(total_padded / 4 + 2) * 64));
+        H2A_TRY(h2a_reserve(ctx, ctx->aff_c, ((size_t)2 * n_final + 2) * 64));
         // the two halves of the slot array are independent trees: they run on two streams so that one half's
         // forward / backward kernels fill the latency gap of the other half's totals inversion
         if (!ctx->stream2) H2A_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, ctx->stream_priority));
@@ -758,26 +767,26 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
             H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
             H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
         }
-        const uint32_t half_out0 = total_padded / 4;                                // outputs of round 0 per half
         const uint64_t scratch_elems = (uint64_t)half_out0 + 128ull * AFF_B;       // per half
         const uint64_t totals_elems = scratch_elems / AFF_B + 4096;
         H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, 2 * (scratch_elems + totals_elems) * 32));
         // the second stream starts one phase late (after the first half's round-0 forward pass): the halves then run
         // out of step and each one's latency-bound inversion hides under the other's forward / backward kernel
-        uint8_t* pts_final = nullptr;
         for (int half = 0; half < 2; half++) {
             cudaStream_t hs = half ? ctx->stream2 : st;
             uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p + (size_t)half * (scratch_elems + totals_elems) * 32;
             uint8_t* totals = scratch + scratch_elems * 32;
-            uint8_t* pts_in = nullptr;
-            uint8_t* pts_out = (uint8_t*)ctx->aff_a.p;
+            uint8_t* const ping = (uint8_t*)ctx->aff_a.p + (size_t)half * half_out0 * 64;
+            uint8_t* const pong = (uint8_t*)ctx->aff_b.p + (size_t)half * (half_out0 / 2) * 64;
+            const uint8_t* pts_in = nullptr;                                       // this half's inputs of the round
             uint32_t n_out = half_out0;
             for (int round = 0; round < R; round++) {
-                const size_t o0 = (size_t)half * n_out;                            // first output of this half in this round
+                const size_t o0 = (size_t)half * n_out;                            // first output of this half in this round (slot arithmetic only)
+                uint8_t* pts_out = round == R - 1 ? (uint8_t*)ctx->aff_c.p + (size_t)half * n_final * 64 : ((round & 1) ? pong : ping);
                 const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
                 const uint32_t blocks = (threads + 127) / 128;
                 if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
-                else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
+                else aff_forward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
                 H2A_LAUNCH_CHECK(ctx);
                 if (half == 0 && round == 0) {
                     H2A_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
@@ -785,15 +794,14 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 }
                 aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, hs>>>(totals, blocks * 128);
                 H2A_LAUNCH_CHECK(ctx);
-                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out + 64 * o0);
-                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in + 128 * o0, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out + 64 * o0);
+                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
+                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
                 H2A_LAUNCH_CHECK(ctx);
                 pts_in = pts_out;
-                pts_out = (pts_in == (uint8_t*)ctx->aff_a.p) ? (uint8_t*)ctx->aff_b.p : (uint8_t*)ctx->aff_a.p;
                 n_out /= 2;
             }
-            pts_final = pts_in;
         }
+        uint8_t* const pts_final = (uint8_t*)ctx->aff_c.p;
         H2A_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
         H2A_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         uint8_t* pts_in = pts_final;

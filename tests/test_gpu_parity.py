@@ -308,6 +308,23 @@ def test_msm_grouped_columns(ctx, orc, c, group):
         hb.free()
 
 
+def test_msm_deep_tree_two_streams(ctx, orc):
+    """2^20 points over tables of width 16: 512 entries per bucket, five rounds of the batched-affine tree.  The two halves
+    of the tree run on two unordered streams; with a point array shared between them a half that got a round ahead
+    overwrote points the other was still reading (wrong sums now and then).  Each half owns its arrays now: every repeat
+    must give the oracle's value."""
+    n = 1 << 20
+    bases = orc.gen_bases(910, n)
+    cols = [orc.gen_scalars(920 + j, n) for j in range(3)]
+    want = [bytes(orc.msm(bases, c)) for c in cols]
+    hb = ctx.upload_bases(bases).precompute(16)
+    try:
+        for rep in range(4):
+            assert [bytes(ctx.msm(hb, c)) for c in cols] == want, rep
+    finally:
+        hb.free()
+
+
 def test_msm_linearity_at_bench_size(ctx):
     """2^22 points (BASELINE metric size): MSM(s, B) over [0,n) equals the sum of MSMs over two halves,
     and MSM with all-one scalars over the first 2^16 bases equals the plain point sum."""
