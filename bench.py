@@ -291,13 +291,14 @@ def main():
             import prove_bench
 
             class _A:
-                k, steps, lookups, precompute = args.prove_k, 2, 9, -1
+                k, steps, lookups, precompute = args.prove_k, 2, 9, prove_bench.PROVER_TABLE_BITS
             bases.free()
             del d_bases, d_scal
             torch.cuda.empty_cache()
             pr = prove_bench.run(ctx, _A)
             line["prove"] = {"metric": pr["metric"], "value": pr["value"], "unit": "s", "higher_is_better": False,
-                             "proof_verifies": pr["proof_verifies"], "phases_ms": pr["phases_ms"], "workload": pr["config"]["workload"]}
+                             "proof_verifies": pr["proof_verifies"], "phases_ms": pr["phases_ms"], "workload": pr["config"]["workload"],
+                             "msm_tables": pr["config"]["msm_tables"]}
             bases = None
         if not args.no_cpu_baseline and world == 1:
             from oracle import loader as orc

@@ -1075,6 +1075,13 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     if (proof_cap < h2a_proof_len(c)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: output buffer too small");
     if ((s.n_instance && !instance_cols) || (s.n_advice && !advice_cols)) return H2A_ERR_INVALID;
     cudaStream_t st = ctx->stream;
+    // the per-call MSM / NTT phase events (h2a_set_profiling) end in a stream synchronisation each: inside a proof that
+    // would serialise the transform lane against the host, and the proof has its own phase events (Stepper)
+    struct ProfOff {
+        h2a_ctx* c; bool saved;
+        explicit ProfOff(h2a_ctx* c_) : c(c_), saved(c_->profiling) { c->profiling = false; }
+        ~ProfOff() { c->profiling = saved; }
+    } prof_off(ctx);
     Stepper steps{ctx};
     steps.mark("start");
 
