@@ -95,6 +95,7 @@ def test_argument_errors_without_a_device():
     assert lib.h2a_init(None, 0) == -1
     assert lib.h2a_destroy(None) == -1
     assert lib.h2a_blinds_len(None) == 0 and lib.h2a_proof_len(None) == 0
+    assert lib.h2a_msm_set_group(None, 8, 2) == -1 and lib.h2a_msm_set_host_split(None, 2) == -1
 
 
 def test_permutation_assembly_cycles():
