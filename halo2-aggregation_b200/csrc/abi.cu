@@ -7,6 +7,7 @@
 
 #include "ctx.hpp"
 #include "host_bn254.hpp"
+#include "tree_layout.hpp"
 
 int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
                 const uint8_t omega[32], int inverse, const uint8_t* coset_shift);
@@ -102,6 +103,16 @@ int h2a_msm_set_group(h2a_ctx* ctx, int cols, int cols_host) {
     if (!ctx || cols < 1 || cols > 64 || cols_host < 1 || cols_host > 64) return H2A_ERR_INVALID;
     ctx->msm_group_cols = cols;
     ctx->msm_group_cols_host = cols_host;
+    return H2A_OK;
+}
+
+int h2a_tree_layout(uint64_t total_padded, int rounds, int half, int round, int64_t out6[6]) {
+    if (!out6 || rounds < 1 || rounds > 5 || half < 0 || half > 1 || round < 0 || round >= rounds) return H2A_ERR_INVALID;
+    if (total_padded == 0 || total_padded % ((uint64_t)2 << rounds)) return H2A_ERR_INVALID;   // msm.cu rounds it up to 2^(R+1)
+    TreeSpan in, out;
+    tree_round_spans(total_padded, rounds, half, round, &in, &out);
+    out6[0] = in.array; out6[1] = (int64_t)in.first; out6[2] = (int64_t)in.count;
+    out6[3] = out.array; out6[4] = (int64_t)out.first; out6[5] = (int64_t)out.count;
     return H2A_OK;
 }
 

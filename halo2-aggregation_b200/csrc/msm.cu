@@ -27,6 +27,7 @@
 #include "ctx.hpp"
 #include "curve.cuh"
 #include "host_bn254.hpp"
+#include "tree_layout.hpp"
 
 using namespace h2a;
 
@@ -776,13 +777,14 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
             cudaStream_t hs = half ? ctx->stream2 : st;
             uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p + (size_t)half * (scratch_elems + totals_elems) * 32;
             uint8_t* totals = scratch + scratch_elems * 32;
-            uint8_t* const ping = (uint8_t*)ctx->aff_a.p + (size_t)half * half_out0 * 64;
-            uint8_t* const pong = (uint8_t*)ctx->aff_b.p + (size_t)half * (half_out0 / 2) * 64;
-            const uint8_t* pts_in = nullptr;                                       // this half's inputs of the round
+            uint8_t* const arrays[3] = {(uint8_t*)ctx->aff_a.p, (uint8_t*)ctx->aff_b.p, (uint8_t*)ctx->aff_c.p};
             uint32_t n_out = half_out0;
             for (int round = 0; round < R; round++) {
                 const size_t o0 = (size_t)half * n_out;                            // first output of this half in this round (slot arithmetic only)
-                uint8_t* pts_out = round == R - 1 ? (uint8_t*)ctx->aff_c.p + (size_t)half * n_final * 64 : ((round & 1) ? pong : ping);
+                TreeSpan in_span, out_span;
+                tree_round_spans(total_padded, R, half, round, &in_span, &out_span);   // tree_layout.hpp: the halves share no region
+                const uint8_t* pts_in = round ? arrays[in_span.array] + 64 * in_span.first : nullptr;
+                uint8_t* pts_out = arrays[out_span.array] + 64 * out_span.first;
                 const uint32_t threads = (uint32_t)((((uint64_t)n_out + 32ull * AFF_B - 1) / (32ull * AFF_B)) * 32);   // whole warps
                 const uint32_t blocks = (threads + 127) / 128;
                 if (round == 0) aff_forward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals);
@@ -797,7 +799,6 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
                 else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
                 H2A_LAUNCH_CHECK(ctx);
-                pts_in = pts_out;
                 n_out /= 2;
             }
         }

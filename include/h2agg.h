@@ -263,6 +263,11 @@ int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void*
  * 6 canonical integer -> Montgomery form, 7 Montgomery form -> canonical integer, 8 inverse by division steps
  * (the one every kernel uses). */
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
+/* Test hook, no device needed: the spans of points half `half` (0/1) of the batched-affine addition tree reads and writes in
+ * round `round` of `rounds`, for a tree of `total_padded` slots (csrc/tree_layout.hpp).  out6 = {in array, in first, in count,
+ * out array, out first, out count}; arrays 0/1/2 are the three point arrays, -1 the sorted entries.  The halves run on two
+ * unordered streams, so their spans must never meet before the join: tests/test_abi_cpu.py checks that. */
+int h2a_tree_layout(uint64_t total_padded, int rounds, int half, int round, int64_t out6[6]);
 /* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* Per-phase device times of the most recent MSM / NTT on this ctx, measured with CUDA events on the

@@ -137,3 +137,43 @@ def test_permutation_assembly_cycles():
         asm.copy(n_cols, 0, 0, 0)
     with pytest.raises(h2a.H2AError):
         asm.copy(0, n, 0, 0)
+
+
+def test_tree_halves_never_share_a_region():
+    """The two halves of the MSM's addition tree run on two unordered streams (csrc/msm.cu): whatever one half writes in any
+    round must be disjoint from everything the other half reads or writes in any round, each half must read exactly what it
+    wrote the round before, and the last round must leave the points contiguous (half 0 then half 1) in the common array."""
+    import ctypes
+    lib = h2a.load_library()
+
+    def spans(total, R, half, rnd):
+        out = (ctypes.c_int64 * 6)()
+        assert lib.h2a_tree_layout(ctypes.c_uint64(total), R, half, rnd, out) == 0
+        return tuple(out[:3]), tuple(out[3:])
+
+    def overlap(a, b):
+        return a[0] == b[0] and a[0] >= 0 and a[1] < b[1] + b[2] and b[1] < a[1] + a[2]
+
+    for R in range(1, 6):
+        unit = 2 << R
+        for total in (unit, 3 * unit, 17 * unit, 1000 * unit, ((17791234 + unit - 1) // unit) * unit):
+            acc = {0: [], 1: []}                                    # every span a half touches, with (span, is_write)
+            for half in (0, 1):
+                prev_out = None
+                for rnd in range(R):
+                    i, o = spans(total, R, half, rnd)
+                    assert o[2] == (total // 4) >> rnd
+                    if rnd == 0:
+                        assert i[0] == -1 and i[1] == half * (total // 2) and i[2] == total // 2
+                    else:
+                        assert i == prev_out                       # reads exactly what it wrote the round before
+                        acc[half].append((i, False))
+                    acc[half].append((o, True))
+                    prev_out = o
+                assert prev_out[0] == 2 and prev_out[1] == half * (total >> (R + 1)) and prev_out[2] == total >> (R + 1)
+            for a, a_w in acc[0]:
+                for b, b_w in acc[1]:
+                    assert not ((a_w or b_w) and overlap(a, b)), (R, total, a, b)
+    bad = (ctypes.c_int64 * 6)()
+    assert lib.h2a_tree_layout(ctypes.c_uint64(96), 5, 0, 0, bad) == -1    # not a multiple of 2^(R+1)
+    assert lib.h2a_tree_layout(ctypes.c_uint64(64), 5, 0, 5, bad) == -1    # round out of range
