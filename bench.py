@@ -8,11 +8,20 @@ per-rank partial results are allgathered (NCCL) and summed on every rank.  `valu
 scalars and bases resident in HBM; `e2e` times the C-ABI call with HOST scalars (pinned), i.e. with the
 host->device copy of the scalars and the device->host read of the result inside the timed region (bases
 stay resident, as `Params` do across the commitments of one proof).
+
+Parity gate: before a line is printed the timed result is compared with the CPU oracle (`oracle/`, the restatement of
+halo2 `best_multiexp` / `best_fft`) on the same inputs, at the benchmark's own size; a mismatch aborts the run.
+
+Next to the headline the line carries, each with its own roofline fractions and same-run CPU figure:
+  `strong`   one fixed 2^22-point and one fixed 2^24-point MSM split over the N ranks (point ranges),
+  `ntt`      Fr NTT at k=22 and the k=20 -> 2^22 coset extension (N = 1 only: a transform does not shard),
+  `prove`    the k=20 prover pipeline at every N (column-parallel commitments + sharded transforms under torchrun),
+  `batch`    64 proofs proved + verify-accumulated, one share per rank (BASELINE config 5),
+  `e2e_cold` bases upload + window-table build + first MSM from host scalars.
 `--impl reference` times the CPU restatement of the reference's path (oracle/, halo2 `best_multiexp`)
 on the host cores instead.
 """
 import argparse
-import ctypes
 import json
 import os
 import statistics
@@ -29,7 +38,7 @@ METRIC = "G1 MSM Mpts/s at 2^22"
 UNIT = "Mpts/s"
 ALGO_BYTES_PER_POINT = 96          # 64 B affine base + 32 B scalar, each read once
 MODMUL_PER_ADD = 6                 # batched affine addition: 3 (Montgomery's trick) + 2M + 1S
-ACCUMULATE_DRAM_BYTES = None       # dram bytes of the accumulation kernels per MSM, from profiles/ (ncu --set full)
+NTT_BYTES_PER_ELEMENT = 64         # one read + one write of every element for the whole transform
 
 
 def clocks_monitor_start(dev_index):
@@ -76,21 +85,12 @@ def clocks_monitor_stop(proc, t_begin, t_end):
             "window": window, "reasons": reasons}
 
 
-def cpu_msm_baseline(orc, target_seconds=15.0):
-    """Oracle `best_multiexp` restatement on all host threads over a bounded prefix of the workload."""
-    threads = orc.hw_threads()
-    n = 1 << 16
-    bases, scalars = orc.gen_bases(1, n), orc.gen_scalars(2, n)
-    t0 = time.perf_counter(); orc.msm(bases, scalars, threads=threads); t = time.perf_counter() - t0
-    rate = n / t
-    log_n = 22
-    while log_n > 16 and (1 << log_n) / rate > target_seconds:
-        log_n -= 2
-    n = 1 << log_n
-    bases, scalars = orc.gen_bases(1, n), orc.gen_scalars(2, n)
-    t0 = time.perf_counter(); orc.msm(bases, scalars, threads=threads); t = time.perf_counter() - t0
-    return {"value": n / t / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "first 2^%d points of the workload, one best_multiexp call, %.2f s" % (log_n, t)}, (bases, scalars)
+def oracle_sum(orc, points64):
+    """Sum of 64-byte affine points with the oracle's own group law (rank-ordered, like the library's combine)."""
+    acc = np.zeros(64, np.uint8)
+    for i in range(points64.size // 64):
+        acc = orc.g1_add(acc, points64[64 * i:64 * i + 64])
+    return acc
 
 
 def run_reference(args, rank, world):
@@ -98,7 +98,7 @@ def run_reference(args, rank, world):
         return
     from oracle import loader as orc
     threads = orc.hw_threads()
-    log_n = min(args.log_n, args.ref_log_n)
+    log_n = args.ref_log_n if args.ref_log_n else args.log_n
     n = 1 << log_n
     bases, scalars = orc.gen_bases(1, n), orc.gen_scalars(2, n)
     for _ in range(args.warmup):
@@ -128,10 +128,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=22)
-    ap.add_argument("--ref-log-n", type=int, default=20, help="points per step of the CPU reference arm")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="points per step of the CPU reference arm (0 = --log-n, the same workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU timings (the oracle parity gate still runs)")
     ap.add_argument("--no-precompute", action="store_true", help="plain Pippenger without the per-Params window tables")
     ap.add_argument("--no-prove", action="store_true", help="skip the k=20 prover pipeline measurement (the metric's first half)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong / ntt / batch / e2e_cold blocks")
     ap.add_argument("--prove-k", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -145,6 +146,7 @@ def main():
 
     import torch
     import halo2_aggregation_b200 as h2a
+    from oracle import loader as orc      # the checker (parity gate) and the cpu_baseline leg only
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU baseline)")
@@ -156,7 +158,46 @@ def main():
     ctx = h2a.Context(local_rank)
     ctx.set_profiling(True)
     n = 1 << args.log_n
+    cpu_threads = max(1, orc.hw_threads() // world)     # all ranks check at once
 
+    def combine(partial):
+        return h2a.allgather_sum(partial, device="cuda") if world > 1 else partial
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.sync()
+
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def timed(fn, steps, kind=0):
+        phases = []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count()
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+            phases.append(ctx.last_phases(kind))
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max(e0.elapsed_time(e1), 0.0)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), ctx.launch_count() - l0, phases, out
+
+    def all_ranks_ok(ok):
+        if world == 1:
+            return ok
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(int(t[0]))
+
+    # ---------------------------------------------------------------------------------------------- headline (weak)
     # this rank's point range [rank*n, (rank+1)*n) of the global MSM, generated in place in HBM
     d_bases = torch.empty(64 * n, dtype=torch.uint8, device="cuda")
     d_scal = torch.empty(32 * n, dtype=torch.uint8, device="cuda")
@@ -165,9 +206,6 @@ def main():
     bases = ctx.bases_from_device(d_bases.data_ptr(), n)
     if not args.no_precompute:
         bases.precompute(-1)   # window tables 2^(c*w) * P_i, built once per Params (h2a_bases_precompute)
-
-    def combine(partial):
-        return h2a.allgather_sum(partial, device="cuda") if world > 1 else partial
 
     def step_dev():
         return combine(ctx.msm_dev(bases, d_scal.data_ptr(), n))
@@ -179,37 +217,9 @@ def main():
     def step_e2e():
         return combine(ctx.msm(bases, host_np))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ctx.sync()
-
-    stream = torch.cuda.ExternalStream(ctx.stream)
-
-    def timed(fn, steps):
-        phases = []
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launch_count()
-        e0.record(stream)
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            out = fn()
-            phases.append(ctx.last_phases(0))
-        e1.record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        ms = max(ms, 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), ctx.launch_count() - l0, phases, out
-
     mon = clocks_monitor_start(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
-        r_dev = step_dev()
+        step_dev()
     t_begin = time.time()
     ms_total, wall_ms, launches, phases, result = timed(step_dev, args.steps)
     t_end = time.time()
@@ -225,25 +235,48 @@ def main():
     e2e_ms, e2e_wall, _, _, r_e2e = timed(step_e2e, args.steps)
     assert bytes(r_e2e) == bytes(result), "e2e and device-resident results differ"
 
+    # ---------------------------------------------------------------------------------------------- parity gate
+    # the oracle's best_multiexp over this rank's own inputs (downloaded from HBM: the very bytes the kernels read)
+    host_bases = d_bases.cpu().numpy()
+    mine = ctx.msm_dev(bases, d_scal.data_ptr(), n)
+    t0 = time.perf_counter()
+    want_mine = orc.msm(host_bases, host_np, threads=cpu_threads)
+    cpu_msm_s = time.perf_counter() - t0
+    ok = bytes(mine) == bytes(want_mine)
+    if world > 1:
+        allw = h2a.allgather_points(want_mine, device="cuda")
+        ok = ok and bytes(oracle_sum(orc, allw)) == bytes(result)
+    else:
+        ok = ok and bytes(result) == bytes(want_mine)
+    if not all_ranks_ok(ok):
+        raise SystemExit("bench.py: PARITY FAILURE — the timed MSM result differs from the oracle's best_multiexp on the same inputs")
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = {"value": n / cpu_msm_s / 1e6, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                        "sample": "the whole workload: one best_multiexp (oracle/ restatement) over the same 2^%d points, %.2f s" % (args.log_n, cpu_msm_s)}
+    del host_bases
+
     total_pts = n * world
     ms_per_step = ms_total / args.steps
     value = total_pts / (ms_per_step * 1e-3) / 1e6
     e2e_value = total_pts / (e2e_ms / args.steps * 1e-3) / 1e6
 
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    imad_peak = ctx.bench_imad()
+    modmul_peak = ctx.bench_modmul()
+
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except OSError:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
         names = [p[0] for p in phases[0]]
         avg = {nm: sum(ph[i][1] for ph in phases) / len(phases) for i, nm in enumerate(names)}
         acc_ms = avg.get("accumulate+merge", 0.0)
-        imad_peak = ctx.bench_imad()
-        modmul_peak = ctx.bench_modmul()
         if args.no_precompute:
             c = 16 if args.log_n >= 17 else 15
         else:
@@ -262,9 +295,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 (254-bit Montgomery)", "data": "synthetic",
+            "parity_checked": "oracle",
+            "parity": "timed result == oracle best_multiexp over the same 2^%d points per rank (and the oracle's sum of the per-rank results), "
+                      "checked before this line was printed" % args.log_n,
             "config": {"workload": "msm_g1 2^%d points per GPU (point-range shard of one %d-point MSM; 64-B partials allgathered and summed)" % (args.log_n, total_pts),
                        "curve": "BN254 G1", "window_bits": c, "windows": windows,
-                       "bases": "resident in HBM" + ("" if args.no_precompute else " with per-Params window tables 2^(c*w)*P_i (%.1f GB, built once by h2a_bases_precompute, outside the timed region)" % (windows * n * 64 / 1e9)),
+                       "bases": "resident in HBM" + ("" if args.no_precompute else " with per-Params window tables 2^(c*w)*P_i (%.1f GB, built once by h2a_bases_precompute, outside the timed region; see e2e_cold)" % (windows * n * 64 / 1e9)),
                        "l2": "inputs %.0f MB per step exceed the 126 MB L2" % (ALGO_BYTES_PER_POINT * n / 1e6),
                        "e2e_bases": "resident in HBM (uploaded once, like Params); scalars come from pinned host memory every step"},
             "clocks": clocks,
@@ -275,7 +311,7 @@ def main():
             "batched": {"value": total_pts / (bat_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": bat_ms / args.steps,
                         "note": "the same %d MSMs through h2a_msm_g1_batch_dev (two pipelined lanes); not the headline value" % args.steps},
             "phases_ms": avg,
-            "roofline": {"kernel": "bucket accumulation: aff_forward_kernel / aff_invert_totals_kernel / aff_backward_kernel rounds + msm_accumulate_pts_kernel",
+            "roofline": {"kernel": "bucket accumulation: batched-affine addition tree (aff_* kernels) + msm_accumulate_pts_kernel",
                          "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak if hbm_peak else None, "traffic": traffic, "peak_source": peak_src,
                          "launch_ms": acc_ms,
@@ -285,32 +321,38 @@ def main():
                          "frac": giga_mul / modmul_peak if modmul_peak else None,
                          "peak_source": "h2a_bench_modmul micro-benchmark, same run (IMAD.WIDE-bound; 32-bit IMAD peak %.1f T/s)" % imad_peak,
                          "algorithmic": "%d additions x %d products (batched affine)" % (adds, MODMUL_PER_ADD)},
+            "cpu_baseline": cpu_baseline,
         }
-        if world == 1 and not args.no_prove:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import prove_bench
 
-            class _A:
-                k, steps, lookups, precompute = args.prove_k, 2, 9, prove_bench.PROVER_TABLE_BITS
-            bases.free()
-            del d_bases, d_scal
-            torch.cuda.empty_cache()
-            pr = prove_bench.run(ctx, _A)
-            line["prove"] = {"metric": pr["metric"], "value": pr["value"], "unit": "s", "higher_is_better": False,
-                             "proof_verifies": pr["proof_verifies"], "phases_ms": pr["phases_ms"], "workload": pr["config"]["workload"],
-                             "msm_tables": pr["config"]["msm_tables"]}
-            bases = None
-        if not args.no_cpu_baseline and world == 1:
-            from oracle import loader as orc
-            line["cpu_baseline"], _ = cpu_msm_baseline(orc)
-        elif world > 1:
-            line["cpu_baseline"] = None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_extras
+    from oracle import plonk as pk        # the oracle's verifier: checker of the proofs the blocks below produce
+    from oracle import pymodel as pm
+    env = dict(ctx=ctx, h2a=h2a, orc=orc, pk=pk, pm=pm, torch=torch, dist=dist, rank=rank, world=world, local_rank=local_rank, args=args,
+               timed=timed, barrier=barrier, combine=combine, all_ranks_ok=all_ranks_ok, hbm_peak=hbm_peak, peak_src=peak_src,
+               modmul_peak=modmul_peak, cpu_threads=cpu_threads)
+    extras = {}
+    if not args.no_extras:
+        # strong scaling reuses the headline's resident inputs at N = 1
+        extras["strong"] = bench_extras.strong_block(env, headline=(bases, d_scal, n, value, ms_per_step, result))
+        if world == 1:
+            extras["e2e_cold"] = bench_extras.cold_block(env, d_bases, host_np, n, result)
+    bases.free()
+    del d_bases, d_scal, host_scal, host_np
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        if world == 1:
+            extras["ntt"] = bench_extras.ntt_block(env)
+        extras["batch"] = bench_extras.batch_block(env)
+    if not args.no_prove:
+        extras["prove"] = bench_extras.prove_block(env)
+    if line is not None:
+        line.update(extras)
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if bases is not None:
-        bases.free()
     ctx.close()
 
 

@@ -257,8 +257,9 @@ class Context:
         return out
 
     # ---- NTT
-    def ntt(self, a, log_n, omega, inverse=False, coset_shift=None):
-        a = _bytes(a).copy()
+    def ntt(self, a, log_n, omega, inverse=False, coset_shift=None, inplace=False):
+        """`inplace`: transform the caller's buffer (e.g. pinned memory) as the C ABI does, instead of a copy."""
+        a = _bytes(a) if inplace else _bytes(a).copy()
         if a.size != 32 << log_n:
             raise H2AError(-1, "ntt: buffer has %d bytes, expected %d" % (a.size, 32 << log_n))
         cs = _bytes(coset_shift) if coset_shift is not None else None
@@ -395,7 +396,7 @@ class Circuit:
         ctx._check(ctx.lib.h2a_circuit_create(ctx.h, _ptr(words), c_sz(words.size), _ptr(consts) if consts.size else None,
                                               c_sz(len(shape.constants)), ctypes.byref(h)))
         self.h = h
-        self.n_instance = shape.num_instance
+        self.n_instance, self.n_advice, self.n = shape.num_instance, shape.num_advice, 1 << shape.k
 
     def free(self):
         if self.h:
@@ -450,6 +451,10 @@ class Circuit:
         ic, ac, bl = _bytes(instance_cols), _bytes(advice_cols), _bytes(blinds)
         if bl.size != 32 * self.blinds_len():
             raise H2AError(-1, "prove: blinds has %d elements, expected %d" % (bl.size // 32, self.blinds_len()))
+        # the C entry point reads n_instance / n_advice whole columns of 2^k elements
+        if ic.size != 32 * self.n * self.n_instance or ac.size != 32 * self.n * self.n_advice:
+            raise H2AError(-1, "prove: instance / advice buffers hold %d / %d bytes, expected %d / %d"
+                           % (ic.size, ac.size, 32 * self.n * self.n_instance, 32 * self.n * self.n_advice))
         out = np.zeros(self.proof_len(), np.uint8)
         ln = c_sz(0)
         inst = np.zeros(64 * self.n_instance, np.uint8)

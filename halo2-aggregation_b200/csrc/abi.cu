@@ -20,6 +20,7 @@ extern "C" {
 
 // ------------------------------------------------------------------ bases
 int h2a_bases_upload(h2a_ctx* ctx, const uint8_t* affine_xy, size_t n, h2a_bases** out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out || (!affine_xy && n)) return H2A_ERR_INVALID;
     h2a_bases* b = new h2a_bases();
     void* d = nullptr;
@@ -44,6 +45,7 @@ int h2a_bases_upload(h2a_ctx* ctx, const uint8_t* affine_xy, size_t n, h2a_bases
     return H2A_OK;
 }
 int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_bases** out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out || (!d_affine_xy && n)) return H2A_ERR_INVALID;
     h2a_bases* b = new h2a_bases();
     b->d = (const uint8_t*)d_affine_xy;
@@ -53,6 +55,7 @@ int h2a_bases_from_device(h2a_ctx* ctx, const void* d_affine_xy, size_t n, h2a_b
     return H2A_OK;
 }
 int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (bases->table) H2A_CUDA(ctx, cudaFree(bases->table));
@@ -62,6 +65,7 @@ int h2a_bases_free(h2a_ctx* ctx, h2a_bases* bases) {
 }
 size_t h2a_bases_len(const h2a_bases* bases) { return bases ? bases->n : 0; }
 int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases || (!out_affine_xy && bases->n)) return H2A_ERR_INVALID;
     if (!bases->n) return H2A_OK;
     H2A_CUDA(ctx, cudaMemcpyAsync(out_affine_xy, bases->d, 64 * bases->n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -69,6 +73,7 @@ int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine
     return H2A_OK;
 }
 int h2a_bases_precompute(h2a_ctx* ctx, h2a_bases* bases, int window_bits) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases) return H2A_ERR_INVALID;
     if (window_bits == 0) {  // drop the tables
         H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -118,6 +123,7 @@ int h2a_tree_layout(uint64_t total_padded, int rounds, int half, int round, int6
 
 int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,
                    uint8_t out_affine[64]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases || !out_affine || (!d_scalars && n)) return H2A_ERR_INVALID;
     if (offset > bases->n || n > bases->n - offset)
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
@@ -186,6 +192,7 @@ static int msm_host_split(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, c
 
 int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_t* scalars, size_t n,
                uint8_t out_affine[64]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases || !out_affine || (!scalars && n)) return H2A_ERR_INVALID;
     if (offset > bases->n || n > bases->n - offset)
         H2A_FAIL(ctx, H2A_ERR_INVALID, "msm: offset %zu + n %zu exceeds %zu bases", offset, n, bases->n);
@@ -201,6 +208,7 @@ int h2a_msm_g1(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const uint8_
 
 int h2a_msm_g1_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const void* const* d_scalars, const size_t* n, int m,
                          uint8_t* out_affine) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases || !d_scalars || !n || !out_affine || m < 0) return H2A_ERR_INVALID;
     for (int j = 0; j < m; j++)
         if (n[j] > bases->n) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm batch: column %d has %zu scalars for %zu bases", j, n[j], bases->n);
@@ -210,6 +218,7 @@ int h2a_msm_g1_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const void* const
 // host scalars: column j is copied on its lane's stream while the other lane computes
 int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* scalars, const size_t* n, int m,
                      uint8_t* out_affine) {
+    H2A_DEVICE(ctx);
     if (!ctx || !bases || !scalars || !n || !out_affine || m < 0) return H2A_ERR_INVALID;
     for (int j = 0; j < m; j++)
         if (n[j] > bases->n) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm batch: column %d has %zu scalars for %zu bases", j, n[j], bases->n);
@@ -255,6 +264,7 @@ int h2a_msm_g1_batch(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const*
 }
 
 int h2a_msm_g1_adhoc(h2a_ctx* ctx, const uint8_t* bases_affine, const uint8_t* scalars, size_t n, uint8_t out_affine[64]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out_affine || ((!bases_affine || !scalars) && n)) return H2A_ERR_INVALID;
     if (n == 0) {
         memset(out_affine, 0, 64);
@@ -288,6 +298,7 @@ int h2a_fr_root_of_unity(uint32_t k, uint8_t out[32]) {
 }
 
 int h2a_ntt_dev(h2a_ctx* ctx, void* d_a, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
+    H2A_DEVICE(ctx);
     if (!ctx || !d_a || !omega) return H2A_ERR_INVALID;
     if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
     const size_t bytes = 32ull << log_n;
@@ -307,6 +318,7 @@ int h2a_ntt_dev(h2a_ctx* ctx, void* d_a, uint32_t log_n, const uint8_t omega[32]
 }
 
 int h2a_ntt(h2a_ctx* ctx, uint8_t* a, uint32_t log_n, const uint8_t omega[32], int inverse, const uint8_t* coset_shift) {
+    H2A_DEVICE(ctx);
     if (!ctx || !a || !omega) return H2A_ERR_INVALID;
     if (log_n < 1 || log_n > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "ntt: log_n=%u not in 1..28", log_n);
     const size_t bytes = 32ull << log_n;
@@ -322,6 +334,7 @@ int h2a_ntt(h2a_ctx* ctx, uint8_t* a, uint32_t log_n, const uint8_t omega[32], i
 
 int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint32_t ext_k, const uint8_t coset_shift[32],
                           uint8_t* out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !coeffs || !out || !coset_shift) return H2A_ERR_INVALID;
     if (k < 1 || ext_k < k || ext_k > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "coeff_to_extended: k=%u ext_k=%u", k, ext_k);
     const size_t in_bytes = 32ull << k, out_bytes = 32ull << ext_k;
@@ -340,6 +353,7 @@ int h2a_coeff_to_extended(h2a_ctx* ctx, const uint8_t* coeffs, uint32_t k, uint3
 
 int h2a_coeff_to_extended_dev(h2a_ctx* ctx, const void* d_coeffs, uint32_t k, uint32_t ext_k, const uint8_t coset_shift[32],
                               void* d_out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !d_coeffs || !d_out || !coset_shift) return H2A_ERR_INVALID;
     if (k < 1 || ext_k < k || ext_k > 28) H2A_FAIL(ctx, H2A_ERR_INVALID, "coeff_to_extended: k=%u ext_k=%u", k, ext_k);
     const size_t in_bytes = 32ull << k, out_bytes = 32ull << ext_k;
@@ -354,6 +368,7 @@ int h2a_coeff_to_extended_dev(h2a_ctx* ctx, const void* d_coeffs, uint32_t k, ui
 }
 
 int h2a_extended_to_coeff_dev(h2a_ctx* ctx, void* d_ext, uint32_t ext_k, const uint8_t coset_shift[32]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !d_ext || !coset_shift) return H2A_ERR_INVALID;
     uint8_t omega[32];
     if (ext_k < 1 || h2a_fr_root_of_unity(ext_k, omega) != H2A_OK) H2A_FAIL(ctx, H2A_ERR_INVALID, "extended_to_coeff: ext_k=%u", ext_k);
@@ -361,6 +376,7 @@ int h2a_extended_to_coeff_dev(h2a_ctx* ctx, void* d_ext, uint32_t ext_k, const u
 }
 
 int h2a_extended_to_coeff(h2a_ctx* ctx, uint8_t* ext, uint32_t ext_k, const uint8_t coset_shift[32]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !ext || !coset_shift) return H2A_ERR_INVALID;
     uint8_t omega[32];
     if (h2a_fr_root_of_unity(ext_k, omega) != H2A_OK || ext_k < 1)

@@ -95,6 +95,13 @@ struct h2a_bases {
         }                                                                                                \
     } while (0)
 
+// Every public entry point first binds the calling thread to the ctx's GPU: two ctxs on different GPUs in one process, or a host
+// framework that changed the current device, must not send allocations and launches to the wrong device.
+#define H2A_DEVICE(ctx)                           \
+    do {                                          \
+        if (ctx) cudaSetDevice((ctx)->device);    \
+    } while (0)
+
 #define H2A_TRY(expr)             \
     do {                          \
         int _rc = (expr);         \

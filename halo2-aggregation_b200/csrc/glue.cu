@@ -101,6 +101,7 @@ using dev::small_msm_kernel;
 // n_sums independent sums: sum s covers terms [sum_offsets[s], sum_offsets[s+1]).  Host pointers.
 int h2a_small_msm(h2a_ctx* ctx, const uint8_t* bases, const uint8_t* scalars, const uint32_t* sum_offsets, size_t n_sums,
                   uint8_t* out_affine) {
+    H2A_DEVICE(ctx);
     if (n_sums == 0) return H2A_OK;
     const size_t n_terms = sum_offsets[n_sums];
     const size_t off_bytes = (n_sums + 1) * 4;
@@ -225,6 +226,7 @@ int h2a_transcript_squeeze_challenge(h2a_transcript* t, uint8_t out_scalar[32]) 
 int h2a_verify_accumulate_batch(h2a_ctx* ctx, size_t n_proofs, const uint8_t* commitments, const int32_t* rotations,
                                 const uint8_t* evals, const size_t* q_off, const uint8_t* ws, const size_t* w_off,
                                 const uint8_t* xuv, const uint8_t omega[32], const uint8_t g1[64], uint8_t* out_efwzw) {
+    H2A_DEVICE(ctx);
     if (!ctx || !commitments || !rotations || !evals || !q_off || !ws || !w_off || !xuv || !omega || !g1 || !out_efwzw)
         return H2A_ERR_INVALID;
     using namespace h2a_host;
@@ -246,6 +248,7 @@ int h2a_verify_accumulate_batch(h2a_ctx* ctx, size_t n_proofs, const uint8_t* co
 int h2a_verify_accumulate(h2a_ctx* ctx, const uint8_t* commitments, const int32_t* rotations, const uint8_t* evals, size_t nq,
                           const uint8_t* ws, size_t n_ws, const uint8_t x[32], const uint8_t u[32], const uint8_t v[32],
                           const uint8_t omega[32], const uint8_t g1[64], uint8_t out_efwzw[256]) {
+    H2A_DEVICE(ctx);
     if (!x || !u || !v) return H2A_ERR_INVALID;
     size_t q_off[2] = {0, nq}, w_off[2] = {0, n_ws};
     uint8_t xuv[96];
@@ -256,6 +259,7 @@ int h2a_verify_accumulate(h2a_ctx* ctx, const uint8_t* commitments, const int32_
 }
 
 int h2a_fold_h(h2a_ctx* ctx, const uint8_t* h_pieces, size_t m, const uint8_t xn[32], uint8_t out_affine[64]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !h_pieces || !xn || !out_affine || m == 0) return H2A_ERR_INVALID;
     using namespace h2a_host;
     TermList tl;

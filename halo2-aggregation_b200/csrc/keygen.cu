@@ -85,6 +85,7 @@ struct Scoped {
 
 int h2a_assembly_sigmas(h2a_ctx* ctx, const h2a_assembly* a, const uint8_t omega[32], const uint8_t delta[32],
                         uint8_t* out_sigmas) {
+    H2A_DEVICE(ctx);
     if (!ctx || !a || !omega || !delta || !out_sigmas) return H2A_ERR_INVALID;
     namespace hh = h2a_host;
     const uint32_t n = 1u << a->k;

@@ -265,6 +265,7 @@ int h2a_init(h2a_ctx** out, int device) {
 }
 
 int h2a_destroy(h2a_ctx* ctx) {
+    H2A_DEVICE(ctx);
     if (!ctx) return H2A_ERR_INVALID;
     if (ctx->alt) {
         h2a_destroy(ctx->alt);
@@ -304,29 +305,34 @@ extern "C" {
 const char* h2a_last_error(const h2a_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 void* h2a_stream(h2a_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int h2a_sync(h2a_ctx* ctx) {
+    H2A_DEVICE(ctx);
     if (!ctx) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2A_OK;
 }
 int h2a_dev_alloc(h2a_ctx* ctx, size_t bytes, void** out_dev) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out_dev) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaSetDevice(ctx->device));
     H2A_CUDA(ctx, cudaMalloc(out_dev, bytes ? bytes : 1));
     return H2A_OK;
 }
 int h2a_dev_free(h2a_ctx* ctx, void* dev) {
+    H2A_DEVICE(ctx);
     if (!ctx) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     H2A_CUDA(ctx, cudaFree(dev));
     return H2A_OK;
 }
 int h2a_copy_h2d(h2a_ctx* ctx, void* dev, const void* host, size_t bytes) {
+    H2A_DEVICE(ctx);
     if (!ctx) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2A_OK;
 }
 int h2a_copy_d2h(h2a_ctx* ctx, void* host, const void* dev, size_t bytes) {
+    H2A_DEVICE(ctx);
     if (!ctx) return H2A_ERR_INVALID;
     H2A_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -334,6 +340,7 @@ int h2a_copy_d2h(h2a_ctx* ctx, void* host, const void* dev, size_t bytes) {
 }
 
 int h2a_gen_scalars_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out) {
+    H2A_DEVICE(ctx);
     if (!ctx || (!d_out && n)) return H2A_ERR_INVALID;
     if (!n) return H2A_OK;
     gen_scalars_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(seed, first, n, (uint8_t*)d_out);
@@ -342,6 +349,7 @@ int h2a_gen_scalars_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, voi
     return H2A_OK;
 }
 int h2a_gen_bases_dev(h2a_ctx* ctx, uint64_t seed, size_t first, size_t n, void* d_out) {
+    H2A_DEVICE(ctx);
     if (!ctx || (!d_out && n)) return H2A_ERR_INVALID;
     if (!n) return H2A_OK;
     gen_bases_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(seed, first, n, (uint8_t*)d_out);
@@ -382,11 +390,13 @@ static int run_elementwise(h2a_ctx* ctx, int kind, int field, int op, const uint
     return H2A_OK;
 }
 int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    H2A_DEVICE(ctx);
     if (field < 0 || field > 1 || op < 0 || op > 8) return H2A_ERR_INVALID;
     if (op <= 2 && !b) return H2A_ERR_INVALID;
     return run_elementwise(ctx, 0, field, op, a, op <= 2 ? b : nullptr, out, n, 32);
 }
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {
+    H2A_DEVICE(ctx);
     if (op < 0 || op > 2) return H2A_ERR_INVALID;
     if (op != 1 && !b) return H2A_ERR_INVALID;
     return run_elementwise(ctx, 1, 0, op, a, op != 1 ? b : nullptr, out, n, 64);
@@ -407,6 +417,7 @@ const char* h2a_phase_name(int kind, int index) { return kind == 0 ? h2a_msm_pha
 uint64_t h2a_launch_count(const h2a_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int h2a_bench_imad(h2a_ctx* ctx, double* out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out) return H2A_ERR_INVALID;
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
     H2A_TRY(h2a_reserve(ctx, ctx->misc, (size_t)blocks * threads * 4));
@@ -431,6 +442,7 @@ int h2a_bench_imad(h2a_ctx* ctx, double* out) {
     return H2A_OK;
 }
 int h2a_bench_modmul(h2a_ctx* ctx, double* out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !out) return H2A_ERR_INVALID;
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 2048;
     H2A_TRY(h2a_reserve(ctx, ctx->misc, (size_t)blocks * threads * 32));

@@ -978,10 +978,13 @@ int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const
     std::vector<int> first(passes + 1, 0);
     for (int q = 0; q < passes; q++) first[q + 1] = first[q] + m / passes + (q < m % passes ? 1 : 0);
 
-    cudaEvent_t ready;
-    H2A_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    H2A_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
-    H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, ready, 0));
+    struct Event {   // released on every exit path
+        cudaEvent_t e = nullptr;
+        ~Event() { if (e) cudaEventDestroy(e); }
+    } ready;
+    H2A_CUDA(ctx, cudaEventCreateWithFlags(&ready.e, cudaEventDisableTiming));
+    H2A_CUDA(ctx, cudaEventRecord(ready.e, ctx->stream));
+    H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, ready.e, 0));
     h2a_ctx* lanes[2] = {ctx, alt};
     int pending_pass[2] = {-1, -1};
     int rc = H2A_OK;
@@ -1015,7 +1018,6 @@ int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const
     ctx->profiling = prof;
     ctx->launches += alt->launches;
     alt->launches = 0;
-    cudaEventDestroy(ready);
     return rc;
 }
 

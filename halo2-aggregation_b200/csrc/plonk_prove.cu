@@ -644,6 +644,7 @@ struct ProverState {
     cudaStream_t ntt_stream = nullptr;
     cudaEvent_t ev_cols_ready = nullptr, ev_ntt_done = nullptr;
     bool overlap_ntt = true;
+    bool ready = false;   // set at the very end of h2a_circuit_set_keys
 };
 
 void h2a_prover_state_free(h2a_ctx* ctx, ProverState* p) {
@@ -854,7 +855,19 @@ extern "C" {
 
 // Loads the proving key: commits the fixed columns and the permutation polynomials (so the vk is set too) and
 // keeps their coefficient and extended-coset forms resident.
+static int set_keys_impl(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const h2a_bases* g_lagrange, const uint8_t* fixed_values,
+                         const uint8_t* sigmas, const uint8_t vk_hash[32], const uint8_t coset_shift[32]);
 int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const h2a_bases* g_lagrange, const uint8_t* fixed_values,
+                         const uint8_t* sigmas, const uint8_t vk_hash[32], const uint8_t coset_shift[32]) {
+    H2A_DEVICE(ctx);
+    const int rc = set_keys_impl(ctx, c, g, g_lagrange, fixed_values, sigmas, vk_hash, coset_shift);
+    if (rc != H2A_OK && ctx && c && c->prover) {   // never leave a half-built proving key behind: create_proof would run on it
+        h2a_prover_state_free(ctx, c->prover);
+        c->prover = nullptr;
+    }
+    return rc;
+}
+static int set_keys_impl(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const h2a_bases* g_lagrange, const uint8_t* fixed_values,
                          const uint8_t* sigmas, const uint8_t vk_hash[32], const uint8_t coset_shift[32]) {
     if (!ctx || !c || !g || !g_lagrange || !vk_hash || !coset_shift) return H2A_ERR_INVALID;
     const Shape& s = c->shape;
@@ -1022,6 +1035,7 @@ int h2a_circuit_set_keys(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     qa.out = p->h_ext;
     H2A_CUDA(ctx, cudaMemcpyAsync(p->d_tab_n, &p->tab_n, sizeof(EvalTables), cudaMemcpyHostToDevice, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->ready = true;
     return H2A_OK;
 }
 
@@ -1035,6 +1049,7 @@ int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* c, int rank, int wor
 }
 
 int h2a_circuit_get_vk(h2a_ctx* ctx, const h2a_circuit* c, uint8_t* fixed_comms, uint8_t* sigma_comms) {
+    H2A_DEVICE(ctx);
     if (!ctx || !c) return H2A_ERR_INVALID;
     if (!c->has_vk) H2A_FAIL(ctx, H2A_ERR_INVALID, "get_vk: no key set");
     if (fixed_comms && !c->fixed_comms.empty()) memcpy(fixed_comms, c->fixed_comms.data(), c->fixed_comms.size());
@@ -1067,9 +1082,10 @@ size_t h2a_proof_len(const h2a_circuit* c) {
 
 int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols, const uint8_t* advice_cols, const uint8_t* blinds,
                      uint8_t* proof_out, size_t proof_cap, size_t* proof_len, uint8_t* inst_comms_out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !c || !proof_out || !proof_len || !blinds) return H2A_ERR_INVALID;
     ProverState* p = c->prover;
-    if (!p) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: no proving key (h2a_circuit_set_keys)");
+    if (!p || !p->ready) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: no proving key (h2a_circuit_set_keys)");
     const Shape& s = c->shape;
     const uint32_t n = s.n, m = 1u << s.ext_k, u = s.usable, bf = s.bf;
     if (proof_cap < h2a_proof_len(c)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: output buffer too small");
@@ -1083,11 +1099,34 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         ~ProfOff() { c->profiling = saved; }
     } prof_off(ctx);
     Stepper steps{ctx};
+    struct Guard {   // on EVERY exit path: nothing of this proof stays in flight on the transform lane (an immediate retry would race
+                     // it on the column buffers and tmp_n[3] / tmp_m), and the phase events are released
+        h2a_ctx* ctx; ProverState* p; Stepper* steps;
+        ~Guard() {
+            if (p->ntt_stream) cudaStreamSynchronize(p->ntt_stream);
+            if (ctx->alt) cudaStreamSynchronize(ctx->alt->stream);
+            for (cudaEvent_t e : steps->ev) cudaEventDestroy(e);
+            steps->ev.clear();
+        }
+    } guard{ctx, p, &steps};
     steps.mark("start");
 
     h2a_glue::Transcript tr;
     size_t pos = 0;
-    auto write_point = [&](const hh::PointA& pt) { tr.common_point(pt); compress_point(pt, proof_out + pos); pos += 32; };
+    // a commitment the transcript absorbs must not be the identity: the verifier's read_point rejects it (and common_point skips
+    // it, so the two transcripts would part ways); returns false then.  The final W_i are written without being absorbed,
+    // as the verifier reads them (src/multiopen.rs:202-218).
+    auto write_point = [&](const hh::PointA& pt) -> bool {
+        const bool ok = tr.common_point(pt);
+        compress_point(pt, proof_out + pos);
+        pos += 32;
+        return ok;
+    };
+    auto write_points = [&](const std::vector<hh::PointA>& pts, const char* what) -> int {
+        for (size_t i = 0; i < pts.size(); i++)
+            if (!write_point(pts[i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: %s commitment %zu is the identity (e.g. an all-zero unblinded column)", what, i);
+        return H2A_OK;
+    };
     auto write_scalar = [&](const hh::Fr& v) { tr.common_scalar(v); uint64_t raw[4]; hh::fr_to_raw(v, raw); memcpy(proof_out + pos, raw, 32); pos += 32; };
     const uint8_t* bl = blinds;
 
@@ -1112,7 +1151,8 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             if (!tr.common_point(cms[i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: instance column %u commits to the identity", i);
             if (inst_comms_out) hh::affine_store(inst_comms_out + 64 * i, cms[i]);
         }
-        for (uint32_t i = 0; i < s.n_advice; i++) write_point(cms[s.n_instance + i]);
+        for (uint32_t i = 0; i < s.n_advice; i++)
+            if (!write_point(cms[s.n_instance + i])) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: advice column %u commits to the identity", i);
     }
     {   // the columns are resident now: their transforms run under the lookup permutations below
         std::vector<Poly3*> cols;
@@ -1165,7 +1205,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         for (auto& l : p->lk) { cols.push_back(l.pa.lag); cols.push_back(l.ps.lag); }
         std::vector<hh::PointA> cms;
         H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
-        for (auto& cm : cms) write_point(cm);
+        H2A_TRY(write_points(cms, "permuted lookup column"));
     }
     steps.mark("lookup permuted columns");
     hh::Fr beta = tr.squeeze(), gamma = tr.squeeze();                              // :390,393
@@ -1233,14 +1273,14 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         for (auto& l : p->lk) cols.push_back(l.z.lag);
         std::vector<hh::PointA> cms;
         H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
-        for (auto& cm : cms) write_point(cm);
+        H2A_TRY(write_points(cms, "grand product"));
     }
     steps.mark("lookup grand products + Z commitments");
     H2A_CUDA(ctx, cudaMemcpyAsync(p->random_coef, bl, 32ull * n, cudaMemcpyHostToDevice, st));   // src/vanishing.rs:54-75
     {
         hh::PointA cm;
         H2A_TRY(commit(ctx, p->g, p->random_coef, n, cm));
-        write_point(cm);                                                           // :419-421
+        if (!write_point(cm)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: the random polynomial commits to the identity");                                                           // :419-421
     }
     hh::Fr y = tr.squeeze();                                                       // :423
 
@@ -1273,20 +1313,12 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         for (uint32_t i = 0; i < s.qdeg; i++) cols.push_back(p->h_coef + 32ull * n * i);
         std::vector<hh::PointA> cms;
         H2A_TRY(commit_batch(ctx, c, p->g, cols, n, cms));
-        for (auto& cm : cms) write_point(cm);
+        H2A_TRY(write_points(cms, "quotient piece"));
     }
     steps.mark("h commitments");
     hh::Fr x = tr.squeeze();                                                       // :436
 
     // ---- evaluations: all requested first, fetched with one copy
-    std::map<int32_t, int> point_slot;                                            // rotation -> slot of x * omega^rot
-    auto point_of = [&](int32_t rot) -> int {
-        auto it = point_slot.find(rot);
-        if (it != point_slot.end()) return it->second;
-        int sl = 8 + (int)point_slot.size();
-        point_slot[rot] = sl;
-        return sl;
-    };
     struct Ev { const uint8_t* coef; int32_t rot; };
     std::vector<Ev> evs;
     for (auto& q : s.iq) evs.push_back({p->instance[q.col].coef, q.rot});
@@ -1302,9 +1334,21 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     for (auto& l : p->lk) {
         evs.push_back({l.z.coef, 0}); evs.push_back({l.z.coef, 1}); evs.push_back({l.pa.coef, 0}); evs.push_back({l.pa.coef, -1}); evs.push_back({l.ps.coef, 0});
     }
-    if (S_EVAL0 + evs.size() + 8 > 1000 || evs.size() > (size_t)MAX_EVALS) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: too many evaluations");
+    if (evs.size() > (size_t)MAX_EVALS) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: too many evaluations");
+    // the evaluation points x * omega^rot live AFTER the evaluation results, so any number of distinct rotations fits as long
+    // as the 1024-slot scalar buffer does (a fixed block in front of the results would run into them at the 9th rotation)
+    const int S_POINT0 = S_EVAL0 + (int)evs.size();
+    std::map<int32_t, int> point_slot;                                            // rotation -> slot of x * omega^rot
+    auto point_of = [&](int32_t rot) -> int {
+        auto it = point_slot.find(rot);
+        if (it != point_slot.end()) return it->second;
+        int sl = S_POINT0 + (int)point_slot.size();
+        point_slot[rot] = sl;
+        return sl;
+    };
     for (auto& e : evs) point_of(e.rot);
     point_of(0);
+    if ((size_t)S_POINT0 + point_slot.size() > 1024) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: %zu evaluations and %zu rotations exceed the scalar buffer", evs.size(), point_slot.size());
     for (auto& kv : point_slot) H2A_TRY(upload_fr(ctx, slot(kv.second), rotate_point(s, x, kv.first)));
     {
         std::vector<dev::EvalReq> reqs(evs.size());
@@ -1378,7 +1422,11 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         std::vector<hh::PointA> part;
         H2A_TRY(commit_batch(ctx, c, p->g, wcols, n, part));
         cms.insert(cms.end(), part.begin(), part.end());
-        for (auto& cm : cms) write_point(cm);                                      // src/multiopen.rs:392
+        for (auto& cm : cms) {                                                     // src/multiopen.rs:392; not absorbed (:202-218)
+            if (hh::is_identity(cm)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: an opening witness W is the identity");
+            compress_point(cm, proof_out + pos);
+            pos += 32;
+        }
     }
     steps.mark("multiopen witnesses");
     *proof_len = pos;
@@ -1392,12 +1440,12 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         p->phase_ms.push_back(ms);
         ctx->prove_phase_names.push_back(steps.names[i]);
     }
-    for (cudaEvent_t e : steps.ev) cudaEventDestroy(e);
-    return H2A_OK;
+    return H2A_OK;   // the guard releases the events
 }
 
 // KZG setup with a caller-supplied secret: g[i] = [s^i] G, g_lagrange[i] = [L_i(s)] G, L_i(s) = omega^i (s^n - 1) / (n (s - omega^i)).
 int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s_[32], h2a_bases** out_g, h2a_bases** out_g_lagrange) {
+    H2A_DEVICE(ctx);
     if (!ctx || !s_ || !out_g || !out_g_lagrange) return H2A_ERR_INVALID;
     if (k < 1 || k > 26) H2A_FAIL(ctx, H2A_ERR_INVALID, "kzg_setup: k=%u not in 1..26", k);
     const uint32_t n = 1u << k;

@@ -117,6 +117,9 @@ inline bool parse_shape(const uint32_t* w, size_t nw, const uint8_t* consts, siz
         p += 3;
         size_t nq = c.type == COL_ADVICE ? s.aq.size() : c.type == COL_FIXED ? s.fq.size() : s.iq.size();
         if (c.type > 2 || c.qidx >= nq) return bad("shape: bad permutation column");
+        // the query must be the one halo2's get_any_query_index(column, Rotation::cur()) returns: this column at rotation 0
+        const Query& q = (c.type == COL_ADVICE ? s.aq : c.type == COL_FIXED ? s.fq : s.iq)[c.qidx];
+        if (q.col != c.col || q.rot != 0) return bad("shape: permutation column does not name its own rotation-0 query");
         s.perm.push_back(c);
     }
     if (p != nw) return bad("shape: trailing words");

@@ -233,6 +233,7 @@ extern "C" {
 
 int h2a_circuit_create(h2a_ctx* ctx, const uint32_t* shape_words, size_t n_words, const uint8_t* constants, size_t n_constants,
                        h2a_circuit** out) {
+    H2A_DEVICE(ctx);
     if (!ctx || !shape_words || !out || (!constants && n_constants)) return H2A_ERR_INVALID;
     h2a_circuit* c = new h2a_circuit();
     std::string err;
@@ -245,6 +246,7 @@ int h2a_circuit_create(h2a_ctx* ctx, const uint32_t* shape_words, size_t n_words
 }
 
 int h2a_circuit_free(h2a_ctx* ctx, h2a_circuit* c) {
+    H2A_DEVICE(ctx);
     if (!ctx || !c) return H2A_ERR_INVALID;
     if (c->prover) h2a_prover_state_free(ctx, c->prover);
     delete c;
@@ -253,6 +255,7 @@ int h2a_circuit_free(h2a_ctx* ctx, h2a_circuit* c) {
 
 int h2a_circuit_set_vk(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* fixed_comms, const uint8_t* sigma_comms,
                        const uint8_t vk_hash[32]) {
+    H2A_DEVICE(ctx);
     if (!ctx || !c || !vk_hash || (!fixed_comms && c->shape.n_fixed) || (!sigma_comms && !c->shape.perm.empty()))
         return H2A_ERR_INVALID;
     c->fixed_comms.assign(fixed_comms, fixed_comms + 64 * (size_t)c->shape.n_fixed);
@@ -264,6 +267,7 @@ int h2a_circuit_set_vk(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* fixed_comms,
 
 int h2a_verify_proof_batch(h2a_ctx* ctx, const h2a_circuit* c, size_t n_proofs, const uint8_t* inst_comms,
                            const uint8_t* const* proofs, const size_t* proof_lens, uint8_t* out_efwzw) {
+    H2A_DEVICE(ctx);
     if (!ctx || !c || !out_efwzw || (n_proofs && (!proofs || !proof_lens)) || (c->shape.n_instance && !inst_comms))
         return H2A_ERR_INVALID;
     if (!c->has_vk) H2A_FAIL(ctx, H2A_ERR_INVALID, "verify: no verifying key set (h2a_circuit_set_vk / h2a_circuit_set_keys)");
@@ -303,6 +307,7 @@ int h2a_verify_proof_batch(h2a_ctx* ctx, const h2a_circuit* c, size_t n_proofs, 
 
 int h2a_verify_proof(h2a_ctx* ctx, const h2a_circuit* c, const uint8_t* inst_comms, const uint8_t* proof, size_t proof_len,
                      uint8_t out_efwzw[256]) {
+    H2A_DEVICE(ctx);
     const uint8_t* proofs[1] = {proof};
     size_t lens[1] = {proof_len};
     return h2a_verify_proof_batch(ctx, c, 1, inst_comms, proofs, lens, out_efwzw);

@@ -163,7 +163,9 @@ int h2a_fold_h(h2a_ctx* ctx, const uint8_t* h_pieces /* m*64 */, size_t m, const
  * evaluate (e, f, w, zw) for ALL proofs of a batch in one device launch.
  * `shape_words`: see csrc/plonk_shape.hpp for the word stream.  `vk_hash`: the transcript scalar derived
  * from `format!("{:?}", vk.pinned())` (src/verifier.rs:341-358) — an input, since the dependency's Debug
- * output cannot be reproduced outside it.  Proof encoding: 32-byte compressed points (x little-endian,
+ * output cannot be reproduced outside it.  TRUST BOUNDARY: the library does not tie `vk_hash` to the shape or to the
+ * fixed / sigma commitments; binding the Fiat-Shamir transcript to the circuit is the caller's job (pass the hash
+ * of the verifying key these commitments belong to).  Proof encoding: 32-byte compressed points (x little-endian,
  * bit 255 = parity of y, identity = zeros) and 32-byte little-endian canonical scalars.
  * H2A_ERR_PROOF: truncated / trailing bytes, a point not on the curve, a non-canonical scalar. */
 typedef struct h2a_circuit h2a_circuit;

@@ -118,6 +118,19 @@ def wide_circuit(k=6, seed=2):
                 public_inputs=[inst[0]])
 
 
+def many_rotations_circuit(k=6, seed=3):
+    """`wide_circuit` with advice queries at eleven more rotations: twelve distinct evaluation points (0, +-1, ..., the
+    z_last rotation), more than the eight a fixed block of point slots in front of the evaluation results could hold."""
+    c = wide_circuit(k=k, seed=seed)
+    sh = c["shape"]
+    extra = [(0, 2), (0, -2), (1, 3), (1, -3), (2, 4), (2, -4), (0, 5), (1, -5), (2, 6), (0, 7), (1, -8)]
+    c["shape"] = pk.Shape(k=sh.k, blinding_factors=sh.bf, degree=sh.degree, num_instance=sh.num_instance, num_advice=sh.num_advice,
+                          num_fixed=sh.num_fixed, advice_queries=sh.advice_queries + extra, fixed_queries=sh.fixed_queries,
+                          instance_queries=sh.instance_queries, gates=sh.gates, constants=sh.constants, lookups=sh.lookups,
+                          perm_columns=sh.perm_columns, coset_shift=sh.coset_shift)
+    return c
+
+
 def setup(orc, circuit, s=0x1234567890abcdef1234567890abcdef, vk_hash=0xC0FFEE):
     shape = circuit["shape"]
     params = pk.Params(orc, shape.k, s)

@@ -95,11 +95,12 @@ def prove_with_library(ctx, orc, c, params, keys, seed):
     return circ, proof, inst, (g, gl)
 
 
-@pytest.mark.parametrize("which,k", [("my_circuit", 6), ("wide", 6), ("my_circuit", 9)])
+@pytest.mark.parametrize("which,k", [("my_circuit", 6), ("wide", 6), ("my_circuit", 9), ("many_rotations", 6)])
 def test_prover_writes_byte_identical_proofs(ctx, orc, which, k):
     """Row a1: same transcript, same commitments, same evaluations, same witnesses -> identical bytes
-    (k = 9 is the reference's own sample size, examples/simple-example.rs:561)."""
-    c = circuits.my_circuit(k=k, table_bits=min(8, k - 2)) if which == "my_circuit" else circuits.wide_circuit(k=k)
+    (k = 9 is the reference's own sample size, examples/simple-example.rs:561; `many_rotations` opens at twelve points)."""
+    c = {"my_circuit": lambda: circuits.my_circuit(k=k, table_bits=min(8, k - 2)), "wide": lambda: circuits.wide_circuit(k=k),
+         "many_rotations": lambda: circuits.many_rotations_circuit(k=k)}[which]()
     params, keys = circuits.setup(orc, c)
     want, want_inst = pk.create_proof(orc, params, c["shape"], keys, c["instance"], c["advice"], seed=5)
     circ, proof, inst, handles = prove_with_library(ctx, orc, c, params, keys, seed=5)
@@ -137,6 +138,33 @@ def test_kzg_setup_matches_oracle(ctx, orc):
     ones = frs_bytes([1] * 1024)
     assert pm.affine_from_bytes(ctx.msm(gl, ones)) == pm.G1
     g.free(); gl.free()
+
+
+def test_prover_rejects_what_the_verifier_would(ctx, orc):
+    """An identity commitment (an all-zero, unblinded advice column) cannot be absorbed by the transcript — the verifier's
+    read_point rejects it — so create_proof fails instead of writing a proof no one can check; short column buffers and
+    a shape whose permutation entry does not name its own rotation-0 query are refused at the boundary."""
+    c = circuits.my_circuit(k=6, table_bits=4)
+    params, keys = circuits.setup(orc, c)
+    circ, proof, inst, handles = prove_with_library(ctx, orc, c, params, keys, seed=5)
+    n = 1 << 6
+    zero_adv = [c["advice"][0], [0] * n]
+    with pytest.raises(h2a.H2AError, match="identity"):
+        circ.prove(cols_bytes(c["instance"]), cols_bytes(zero_adv), frs_bytes(pk.blinds_buffer(c["shape"], 5)))
+    # the failed call left nothing in flight: the same circuit proves again, byte for byte
+    again, _ = circ.prove(cols_bytes(c["instance"]), cols_bytes(c["advice"]), frs_bytes(pk.blinds_buffer(c["shape"], 5)))
+    assert again == proof
+    with pytest.raises(h2a.H2AError):
+        circ.prove(cols_bytes(c["instance"]), cols_bytes(c["advice"])[:-32], frs_bytes(pk.blinds_buffer(c["shape"], 5)))
+    circ.free()
+    for h in handles:
+        h.free()
+    sh = c["shape"]
+    bad = pk.Shape(k=sh.k, blinding_factors=sh.bf, degree=sh.degree, num_instance=1, num_advice=2, num_fixed=4,
+                   advice_queries=sh.advice_queries, fixed_queries=sh.fixed_queries, instance_queries=sh.instance_queries, gates=sh.gates,
+                   constants=[], lookups=sh.lookups, perm_columns=[(circuits.I, 0, 0), (circuits.F, 0, 3), (circuits.A, 0, 1), (circuits.A, 1, 1)])
+    with pytest.raises(h2a.H2AError):
+        h2a.Circuit(ctx, bad, frs_bytes([]))
 
 
 @pytest.mark.parametrize("k", [11, 14])

@@ -111,6 +111,15 @@ def build(ctx, k, n_lookups=9, n_fixed=20, seed=1):
     return s, inst_b, adv_b.reshape(-1), fixed_b, sigmas_b
 
 
+def op_counts(s):
+    """MSMs and transforms of one create_proof over this shape: every committed column is one n-point MSM,
+    one size-n inverse transform and one 4n coset transform; the quotient comes back through one 4n inverse transform."""
+    chunks = (len(s.perm_columns) + s.degree - 3) // (s.degree - 2)
+    rotations = {r for _, r in s.advice_queries + s.fixed_queries + s.instance_queries} | {0, 1, -1, -(s.bf + 1)}
+    cols = s.num_instance + s.num_advice + 3 * len(s.lookups) + chunks
+    return {"msm_n": cols + 1 + (s.degree - 1) + len(rotations), "ifft_n": cols, "coset_fft_4n": cols, "ifft_4n": 1}
+
+
 def random_blinds(ctx, count, seed):
     rng = np.random.default_rng(seed)
     raw = rng.integers(0, 256, size=(count, 32), dtype=np.uint8)
@@ -155,6 +164,8 @@ def run(ctx, args):
     rhs = h2a.g1_sum(np.concatenate([zw, f, e]))
     ok = bytes(lhs) == bytes(rhs)
     best = min(times[1:])
+    fc, sc = circ.get_vk(shape.num_fixed, len(shape.perm_columns))
+    check = dict(shape=shape, fixed_commitments=fc, sigma_commitments=sc, vk_hash=0xC0FFEE, inst=inst, proof=proof, secret=secret)
     circ.free(); g.free(); gl.free()
     return ({"metric": "agg-circuit prove s at k=%d" % args.k, "value": best, "unit": "s", "higher_is_better": False,
                       "steps": args.steps, "all_s": times[1:], "first_call_s": times[0], "proof_bytes": len(proof), "proof_verifies": ok,
@@ -165,7 +176,8 @@ def run(ctx, args):
                                             "aggregation circuit do), so their commitments see mostly-zero windows; the permuted, grand-product, quotient "
                                             "and opening polynomials are full-width field elements",
                                  "msm_tables": args.precompute},
-                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof)})
+                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof),
+                      "op_counts": op_counts(shape), "_check": check, "_efwzw": efwzw})
 
 
 def main():
