@@ -30,7 +30,8 @@ class H2AError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libh2agg.so")
+    """The in-tree build; H2A_LIB names another build of the SAME library (kernel A/B variants made by tools/build_variant.py)."""
+    return os.environ.get("H2A_LIB") or os.path.join(_HERE, "libh2agg.so")
 
 
 def header_path():

@@ -12,6 +12,15 @@
 // chain is a single asm statement: the CC flag never lives across statement boundaries.
 #pragma once
 #include <cstdint>
+#ifdef __CUDACC__
+#include "field_mul_gen.cuh"
+#endif
+// H2A_WIDE_SQR (default 1): sqr() is the generated dedicated square of field_mul_gen.cuh (100 IMAD.WIDE instead of 136:
+// 76.6 against 65.0 G/s in tools/micro/mulvar.cu); 0 squares with the product.  The generated Karatsuba product (112 IMAD.WIDE
+// but 80 more plain instructions) measured slower than the row-interleaved product below and is not used.
+#ifndef H2A_WIDE_SQR
+#define H2A_WIDE_SQR 1
+#endif
 
 namespace h2a {
 
@@ -239,6 +248,20 @@ struct Fp {
 
     // Montgomery product a*b/R mod p, fully reduced.  Inputs < p.
     __device__ __forceinline__ Fp operator*(const Fp& o) const {
+        return mul_cios(o);
+    }
+    __device__ __forceinline__ Fp sqr() const {
+#if H2A_WIDE_SQR
+        Fp r;
+        mont_sqr_wide<F>(r.l, l);
+        reduce_once(r.l);
+        return r;
+#else
+        return mul_cios(*this);
+#endif
+    }
+    // the row-interleaved (CIOS) product: 136 IMAD.WIDE, fewest other instructions
+    __device__ __forceinline__ Fp mul_cios(const Fp& o) const {
         const uint32_t* a = l;
         uint32_t X[8], Y[8];  // X aligned at limb 0, Y aligned at limb 1 (roles swap every row)
         {   // row 0
@@ -282,8 +305,6 @@ struct Fp {
         reduce_once(r.l);
         return r;
     }
-    __device__ __forceinline__ Fp sqr() const { return (*this) * (*this); }
-
     // Montgomery -> canonical integer limbs (multiply by raw 1)
     __device__ __forceinline__ Fp from_mont() const {
         Fp o = zero();
