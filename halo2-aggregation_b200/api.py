@@ -208,6 +208,26 @@ class Context:
         self._check(self.lib.h2a_kzg_setup(self.h, ctypes.c_uint32(k), _ptr(_bytes(s)), ctypes.byref(g), ctypes.byref(gl)))
         return Bases(self, g), Bases(self, gl)
 
+    def params_write(self, path, k, g, g_lagrange, compressed=False, trailer=None):
+        """Params::write: stream (g, g_lagrange) to a parameter file (format: csrc/params.cu)."""
+        tr = None if trailer is None else _bytes(trailer)
+        if tr is not None and tr.size != 128:
+            raise ValueError("trailer must be 128 bytes")
+        self._check(self.lib.h2a_params_write(self.h, os.fsencode(path), ctypes.c_uint32(k), g.h, g_lagrange.h, int(bool(compressed)), _ptr(tr)))
+
+    def params_read(self, path):
+        """Params::read: (k, g, g_lagrange, trailer or None); digest and curve membership are checked on load."""
+        k, g, gl, has = ctypes.c_uint32(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+        tr = np.zeros(128, np.uint8)
+        self._check(self.lib.h2a_params_read(self.h, os.fsencode(path), ctypes.byref(k), ctypes.byref(g), ctypes.byref(gl), _ptr(tr), ctypes.byref(has)))
+        return int(k.value), Bases(self, g), Bases(self, gl), (tr if has.value else None)
+
+    def verifier_params(self, g_lagrange, public_inputs_size):
+        """Setup::verifier_params: a view of the first `public_inputs_size` Lagrange bases (shares g_lagrange's memory)."""
+        h = ctypes.c_void_p()
+        self._check(self.lib.h2a_params_verifier_view(self.h, g_lagrange.h, c_sz(public_inputs_size), ctypes.byref(h)))
+        return Bases(self, h)
+
     def set_msm_window(self, c):
         self._check(self.lib.h2a_msm_set_window(self.h, int(c)))
 

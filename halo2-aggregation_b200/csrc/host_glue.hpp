@@ -28,13 +28,17 @@ class Blake2bState {
         h_[7] ^= p1;
     }
     void absorb(const uint8_t* data, size_t len) {
-        for (size_t i = 0; i < len; i++) {
+        while (len) {
             if (fill_ == 128) {  // a full block is only compressed once more input follows it
                 counter_ += 128;
                 round_block(false);
                 fill_ = 0;
             }
-            block_[fill_++] = data[i];
+            const size_t take = len < 128 - fill_ ? len : 128 - fill_;
+            memcpy(block_ + fill_, data, take);
+            fill_ += take;
+            data += take;
+            len -= take;
         }
     }
     void digest(uint8_t* out) const {  // does not disturb the running state

@@ -241,6 +241,23 @@ int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s[32], h2a_bases** out
 int h2a_xorshift_scalar(const uint8_t seed[16], uint8_t out_scalar[32]);
 /* Copy resident bases back to the host (n * 64 bytes), e.g. to write a params file. */
 int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy);
+/* Parameter files — `Params::write(&mut file)` / `Params::read(file)` as used at examples/simple-example.rs:679-691 to cache
+ * the k = 23 parameters, and `Setup::<Bn256>::verifier_params(&params, public_inputs_size)` (:590, :693).  The dependency's
+ * byte format is not visible from the reference, so the format is this library's (csrc/params.cu has the layout): a 64-byte
+ * header (magic "H2APARAM", version, k, flags), g[0..2^k), g_lagrange[0..2^k) as 64-byte in-memory points or — `compressed`
+ * != 0 — as the proof's 32-byte encoding, an optional opaque 128-byte trailer (the caller's [s]G2), and a Blake2b-512 digest
+ * of everything before it.  Points stream between the file and HBM through pinned staging buffers.  h2a_params_read checks the
+ * digest and, on the device, that every point is on the curve (H2A_ERR_INVALID otherwise, nothing returned); it returns two
+ * resident handles (free with h2a_bases_free).  `trailer128` may be NULL on both sides; *has_trailer says whether the file
+ * carried one. */
+int h2a_params_write(h2a_ctx* ctx, const char* path, uint32_t k, const h2a_bases* g, const h2a_bases* g_lagrange, int compressed,
+                     const uint8_t* trailer128);
+int h2a_params_read(h2a_ctx* ctx, const char* path, uint32_t* out_k, h2a_bases** out_g, h2a_bases** out_g_lagrange,
+                    uint8_t* trailer128, int* has_trailer);
+/* The verifier's parameters: a handle over the first `public_inputs_size` Lagrange bases, against which
+ * `params_verifier.commit_lagrange(public_inputs)` (examples/simple-example.rs:638-640) is one h2a_msm_g1.  Shares the memory of
+ * `g_lagrange`, which must outlive it. */
+int h2a_params_verifier_view(h2a_ctx* ctx, const h2a_bases* g_lagrange, size_t public_inputs_size, h2a_bases** out);
 /* Per-phase device times (ms) of the last h2a_create_proof; returns the number of phases written. */
 int h2a_prove_phase_ms(h2a_ctx* ctx, const h2a_circuit* circuit, float* ms, int cap);
 const char* h2a_prove_phase_name(const h2a_ctx* ctx, int index);
