@@ -8,6 +8,7 @@ SURVEY.md §8b).  There is no CPU fallback: constructing a `Context` without the
 without a B200 raises.
 """
 from .api import (  # noqa: F401
+    comm_unique_id,
     Context,
     Bases,
     Circuit,

@@ -101,6 +101,15 @@ def xorshift_scalar(seed16):
     return out
 
 
+def comm_unique_id():
+    """128 opaque bytes naming a new communicator (rank 0 draws two and hands them to every rank)."""
+    out = np.zeros(128, np.uint8)
+    rc = load_library().h2a_comm_unique_id(_ptr(out))
+    if rc != 0:
+        raise H2AError(rc, "h2a_comm_unique_id failed (libnccl.so.2 not found?)")
+    return out
+
+
 def g1_sum(points):
     pts = _bytes(points)
     out = np.zeros(64, np.uint8)
@@ -227,6 +236,46 @@ class Context:
         h = ctypes.c_void_p()
         self._check(self.lib.h2a_params_verifier_view(self.h, g_lagrange.h, c_sz(public_inputs_size), ctypes.byref(h)))
         return Bases(self, h)
+
+    # ---- several GPUs (the library's own NCCL plumbing, csrc/comm.cu)
+    def comm_init(self, rank, world, ids):
+        """ids: 256 bytes = two h2a_comm_unique_id() results drawn by rank 0 and handed to every rank."""
+        ids = _bytes(ids)
+        if ids.size != 256:
+            raise ValueError("ids must be two 128-byte unique ids")
+        self._check(self.lib.h2a_comm_init(self.h, int(rank), int(world), _ptr(ids[:128].copy()), _ptr(ids[128:].copy())))
+
+    def comm_init_torch(self):
+        """comm_init with the ids passed around through an initialised torch.distributed group."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ids = [np.concatenate([comm_unique_id(), comm_unique_id()]).tobytes() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        self.comm_init(rank, world, np.frombuffer(ids[0], dtype=np.uint8))
+        return rank, world
+
+    def comm_destroy(self):
+        self._check(self.lib.h2a_comm_destroy(self.h))
+
+    def comm_allgather(self, send):
+        send = _bytes(send)
+        world = int(self.lib.h2a_comm_world(self.h))
+        out = np.zeros(send.size * world, np.uint8)
+        self._check(self.lib.h2a_comm_allgather(self.h, _ptr(send), _ptr(out), c_sz(send.size)))
+        return out
+
+    def comm_allgather_dev(self, d_send, d_recv, nbytes):
+        self._check(self.lib.h2a_comm_allgather_dev(self.h, ctypes.c_void_p(d_send), ctypes.c_void_p(d_recv), c_sz(nbytes)))
+
+    def comm_broadcast_dev(self, d_buf, nbytes, root):
+        self._check(self.lib.h2a_comm_broadcast_dev(self.h, ctypes.c_void_p(d_buf), c_sz(nbytes), int(root)))
+
+    def msm_sharded(self, local_bases, d_local_scalars, n_local, offset=0):
+        """One MSM whose point ranges live on the ranks of the communicator; every rank gets the same 64 bytes."""
+        out = np.zeros(64, np.uint8)
+        self._check(self.lib.h2a_msm_g1_sharded(self.h, local_bases.h, c_sz(offset), ctypes.c_void_p(d_local_scalars), c_sz(n_local), _ptr(out)))
+        return out
 
     def set_msm_window(self, c):
         self._check(self.lib.h2a_msm_set_window(self.h, int(c)))
@@ -435,11 +484,17 @@ class Circuit:
                                                           _ptr(s) if s.size else None, _ptr(_bytes(vk_hash)), _ptr(_bytes(coset_shift))))
         self._keep = (g, g_lagrange)
 
-    def set_distribution(self, rank, world, group=None, device=None):
-        """Column-parallel commitments over `world` processes (torch.distributed): every rank proves the same inputs,
-        commits its share of each batch, and the 64-byte results are allgathered."""
+    def set_distribution(self, rank, world, group=None, device=None, native=False):
+        """One proof over `world` processes: every rank proves the same inputs.  native=True uses the library's own
+        communicator (Context.comm_init): commitments column-parallel, transforms column-parallel with the results
+        broadcast, quotient row-parallel.  Otherwise only the commitments are shared and their 64-byte results are
+        allgathered through torch.distributed."""
         if world <= 1:
             self.ctx._check(self.ctx.lib.h2a_circuit_set_distribution(self.ctx.h, self.h, 0, 1, None, None))
+            self._exchange = None
+            return
+        if native:
+            self.ctx._check(self.ctx.lib.h2a_circuit_set_distribution(self.ctx.h, self.h, int(rank), int(world), None, None))
             self._exchange = None
             return
         from .dist import make_commitment_exchange

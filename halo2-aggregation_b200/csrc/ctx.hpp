@@ -63,6 +63,12 @@ struct h2a_ctx {
     } msm_pending;
     h2a_ctx* alt = nullptr;  // second lane (own stream + workspace) for pipelined batches; created on first use
 
+    // multi-GPU plumbing (comm.cu): two NCCL communicators (0: small exchanges on the ctx stream, 1: bulk broadcasts on the
+    // prover's transform lane), this process's rank, and a staging buffer for host-buffer collectives
+    void* comm[2] = {nullptr, nullptr};
+    int comm_rank = 0, comm_world = 1;
+    DevBuf comm_buf;
+
     // NTT workspace
     DevBuf ntt_a, ntt_b;
     std::map<uint32_t, NttTables*> ntt_tables;  // keyed by log_n of the twiddle table
@@ -136,3 +142,9 @@ int h2a_msm_finish(h2a_ctx* ctx, uint8_t* out_affine /* 64 bytes per column of t
 int h2a_msm_batch_dev(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* const* d_scalars, const size_t* n, int m, uint8_t* out_affine,
                       const uint8_t* const* h_src = nullptr);
 int h2a_get_alt(h2a_ctx* ctx, h2a_ctx** out);
+// comm.cu
+bool h2a_comm_active(const h2a_ctx* ctx);
+int h2a_comm_group_start(h2a_ctx* ctx);
+int h2a_comm_group_end(h2a_ctx* ctx);
+int h2a_comm_broadcast_on(h2a_ctx* ctx, int lane, void* d_buf, size_t bytes, int root, cudaStream_t stream);
+int h2a_comm_allgather_on(h2a_ctx* ctx, int lane, const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t stream);

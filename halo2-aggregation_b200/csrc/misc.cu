@@ -273,7 +273,8 @@ int h2a_destroy(h2a_ctx* ctx) {
     }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->scalars, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->buckets, &ctx->segsums,
+    h2a_comm_destroy(ctx);
+    DevBuf* bufs[] = {&ctx->comm_buf, &ctx->scalars, &ctx->offsets, &ctx->cursor, &ctx->sorted, &ctx->buckets, &ctx->segsums,
                       &ctx->winsums, &ctx->heavy,   &ctx->misc,   &ctx->ntt_a,  &ctx->ntt_b,  &ctx->aff_a, &ctx->aff_b, &ctx->aff_c,
                       &ctx->aff_scratch, &ctx->aff_u32};
     for (DevBuf* b : bufs)

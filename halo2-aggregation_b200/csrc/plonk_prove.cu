@@ -63,6 +63,7 @@ struct QuotientArgs {
     uint32_t vanish_mask;
     int32_t last_rot;
     uint8_t* out;
+    uint32_t row_lo, row_hi;                            // rows [row_lo, row_hi) of the extended domain this launch evaluates
 };
 
 namespace dev {
@@ -119,8 +120,8 @@ template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) quotient_kernel(const QuotientArgs* ap) {
     const QuotientArgs& a = *ap;
     const EvalTables& t = a.t;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > t.mask) return;
+    const uint32_t i = a.row_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.row_hi) return;
     const Fr beta = Fr::load(a.beta), gamma = Fr::load(a.gamma), one = Fr::one();
     uint32_t k = 0;                                       // expression counter
     auto w = [&]() { return Fr::load(a.ypow[k++]); };
@@ -643,6 +644,7 @@ struct ProverState {
     // in a phase of their own.  Default priority, i.e. below the ctx streams (misc.cu): it takes the SMs the MSM leaves idle.
     cudaStream_t ntt_stream = nullptr;
     cudaEvent_t ev_cols_ready = nullptr, ev_ntt_done = nullptr;
+    size_t dist_cols_done = 0;   // columns handed to transform_columns so far in this proof (round-robin owner when several GPUs share it)
     bool overlap_ntt = true;
     bool ready = false;   // set at the very end of h2a_circuit_set_keys
 };
@@ -699,6 +701,9 @@ int to_coef(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* lag, uint8_t* coef) {
     hh::fr_store(w, c->shape.omega);
     return h2a_ntt_run(ctx, lag, c->shape.n, c->prover->tmp_n[3], coef, c->shape.k, w, 1, nullptr);
 }
+// One proof over several GPUs through the library's own communicator (h2a_circuit_set_distribution without a callback)
+bool native_dist(const h2a_ctx* ctx, const h2a_circuit* c) { return c->dist_world > 1 && !c->dist_exchange && h2a_comm_active(ctx); }
+
 int to_ext(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* coef, uint8_t* ext) {
     uint8_t w[32];
     hh::fr_store(w, hh::fr_root_of_unity((int)c->shape.ext_k));
@@ -710,10 +715,28 @@ int to_ext(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* coef, uint8_t* ext) {
 int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& cols) {
     ProverState* p = c->prover;
     if (cols.empty()) return H2A_OK;
-    if (!p->overlap_ntt) {
-        for (Poly3* q : cols) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
+    // several GPUs: column q of this proof's running count is transformed by rank q % world only, and its coefficient and
+    // extended forms are broadcast from there (bulk communicator, same stream as the transforms, one NCCL group per call)
+    const bool dist = native_dist(ctx, c);
+    const int W = c->dist_world, me = c->dist_rank;
+    std::vector<int> owner(cols.size(), me);
+    if (dist) for (size_t j = 0; j < cols.size(); j++) owner[j] = (int)((p->dist_cols_done + j) % (size_t)W);
+    p->dist_cols_done += cols.size();
+    const uint32_t n = c->shape.n, m = 1u << c->shape.ext_k;
+    auto run = [&](cudaStream_t lane) -> int {
+        for (size_t j = 0; j < cols.size(); j++)
+            if (owner[j] == me) { H2A_TRY(to_coef(ctx, c, cols[j]->lag, cols[j]->coef)); H2A_TRY(to_ext(ctx, c, cols[j]->coef, cols[j]->ext)); }
+        if (dist) {
+            H2A_TRY(h2a_comm_group_start(ctx));
+            for (size_t j = 0; j < cols.size(); j++) {
+                H2A_TRY(h2a_comm_broadcast_on(ctx, 1, cols[j]->coef, 32ull * n, owner[j], lane));
+                H2A_TRY(h2a_comm_broadcast_on(ctx, 1, cols[j]->ext, 32ull * m, owner[j], lane));
+            }
+            H2A_TRY(h2a_comm_group_end(ctx));
+        }
         return H2A_OK;
-    }
+    };
+    if (!p->overlap_ntt) return run(ctx->stream);
     H2A_CUDA(ctx, cudaEventRecord(p->ev_cols_ready, ctx->stream));
     H2A_CUDA(ctx, cudaStreamWaitEvent(p->ntt_stream, p->ev_cols_ready, 0));
     struct Swap {   // h2a_ntt_run launches on ctx->stream
@@ -721,8 +744,7 @@ int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& c
         Swap(h2a_ctx* c_, cudaStream_t s_) : c(c_), saved(c_->stream) { c->stream = s_; }
         ~Swap() { c->stream = saved; }
     } swap(ctx, p->ntt_stream);
-    for (Poly3* q : cols) { H2A_TRY(to_coef(ctx, c, q->lag, q->coef)); H2A_TRY(to_ext(ctx, c, q->coef, q->ext)); }
-    return H2A_OK;
+    return run(p->ntt_stream);
 }
 // the ctx stream waits for everything queued on the transform lane
 int join_transforms(h2a_ctx* ctx, h2a_circuit* c) {
@@ -746,7 +768,7 @@ int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint3
 int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n,
                  std::vector<hh::PointA>& out, const std::vector<const uint8_t*>* host_src = nullptr) {
     std::vector<uint8_t> pts(64 * cols.size(), 0);
-    if (c->dist_world > 1 && c->dist_exchange) {   // this rank's share of the columns, then the exchange
+    if (c->dist_world > 1 && (c->dist_exchange || h2a_comm_active(ctx))) {   // this rank's share of the columns, then the exchange
         if (host_src)   // every rank needs every column on its device later: copy them all first
             for (size_t j = 0; j < cols.size(); j++)
                 H2A_CUDA(ctx, cudaMemcpyAsync((void*)cols[j], (*host_src)[j], 32ull * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -758,8 +780,15 @@ int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, con
         std::vector<uint8_t> part(64 * mine.size() + 64);
         if (!mine.empty()) H2A_TRY(h2a_msm_batch_dev(ctx, bases, mine.data(), ns.data(), (int)mine.size(), part.data()));
         for (size_t q = 0; q < idx.size(); q++) memcpy(pts.data() + 64 * idx[q], part.data() + 64 * q, 64);
-        if (c->dist_exchange(c->dist_user, pts.data(), cols.size()) != 0)
-            H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: the commitment exchange callback failed");
+        if (c->dist_exchange) {
+            if (c->dist_exchange(c->dist_user, pts.data(), cols.size()) != 0)
+                H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: the commitment exchange callback failed");
+        } else {   // the library's own allgather of raw bytes: slot j comes from its owner, rank j % world
+            std::vector<uint8_t> all(pts.size() * (size_t)c->dist_world);
+            H2A_TRY(h2a_comm_allgather(ctx, pts.data(), all.data(), pts.size()));
+            for (size_t j = 0; j < cols.size(); j++)
+                memcpy(pts.data() + 64 * j, all.data() + pts.size() * (j % (size_t)c->dist_world) + 64 * j, 64);
+        }
     } else {
         std::vector<size_t> ns(cols.size(), n);
         H2A_TRY(h2a_msm_batch_dev(ctx, bases, cols.data(), ns.data(), (int)cols.size(), pts.data(), host_src ? host_src->data() : nullptr));
@@ -1041,6 +1070,8 @@ static int set_keys_impl(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
 
 int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* c, int rank, int world, h2a_exchange_fn exchange, void* user) {
     if (!ctx || !c || world < 1 || rank < 0 || rank >= world) return H2A_ERR_INVALID;
+    if (world > 1 && !exchange && (!h2a_comm_active(ctx) || ctx->comm_world != world || ctx->comm_rank != rank))
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "set_distribution: no exchange callback and no communicator of %d ranks with this rank = %d (h2a_comm_init)", world, rank);
     c->dist_rank = rank;
     c->dist_world = world;
     c->dist_exchange = exchange;
@@ -1110,6 +1141,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         }
     } guard{ctx, p, &steps};
     steps.mark("start");
+    p->dist_cols_done = 0;
 
     h2a_glue::Transcript tr;
     size_t pos = 0;
@@ -1295,13 +1327,19 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         hh::Fr wgt = hh::fr_one();
         for (size_t e = K; e-- > 0;) { hh::fr_store(p->qargs.ypow[e], wgt); wgt = wgt * y; }
     }
+    // several GPUs: rank r evaluates rows [r m / W, (r + 1) m / W) and the slices are allgathered in place
+    const bool q_rows = native_dist(ctx, c) && m % (uint32_t)c->dist_world == 0 && m / (uint32_t)c->dist_world >= 1024;
+    const uint32_t q_cnt = q_rows ? m / (uint32_t)c->dist_world : m;
+    p->qargs.row_lo = q_rows ? q_cnt * (uint32_t)c->dist_rank : 0u;
+    p->qargs.row_hi = p->qargs.row_lo + q_cnt;
     H2A_CUDA(ctx, cudaMemcpyAsync(p->d_qargs, &p->qargs, sizeof(QuotientArgs), cudaMemcpyHostToDevice, st));
     {
         static const int minb = getenv("H2A_QUOTIENT_MINB") ? atoi(getenv("H2A_QUOTIENT_MINB")) : 3;
-        if (minb >= 5) LAUNCH1D(dev::quotient_kernel<5>, m, 128, p->d_qargs);
-        else if (minb == 4) LAUNCH1D(dev::quotient_kernel<4>, m, 128, p->d_qargs);
-        else LAUNCH1D(dev::quotient_kernel<3>, m, 128, p->d_qargs);
+        if (minb >= 5) LAUNCH1D(dev::quotient_kernel<5>, q_cnt, 128, p->d_qargs);
+        else if (minb == 4) LAUNCH1D(dev::quotient_kernel<4>, q_cnt, 128, p->d_qargs);
+        else LAUNCH1D(dev::quotient_kernel<3>, q_cnt, 128, p->d_qargs);
     }
+    if (q_rows) H2A_TRY(h2a_comm_allgather_on(ctx, 0, p->h_ext + 32ull * p->qargs.row_lo, p->h_ext, 32ull * q_cnt, st));
     {   // extended_to_coeff, then h is cut into quotient_poly_degree pieces of n coefficients
         uint8_t w[32];
         hh::fr_store(w, hh::fr_root_of_unity((int)s.ext_k));

@@ -214,6 +214,30 @@ typedef int (*h2a_exchange_fn)(void* user, uint8_t* commitments, size_t m);
 int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* circuit, int rank, int world, h2a_exchange_fn exchange,
                                  void* user);
 
+/* ---- several GPUs --------------------------------------------------------------------------------
+ * One process per GPU, one ctx per process; the library carries its own NCCL plumbing (bound at run time from
+ * libnccl.so.2), so a Rust host needs no other collective library.  Rank 0 draws two unique ids (h2a_comm_unique_id, twice)
+ * and hands them to the other processes over any channel it has; every process then calls h2a_comm_init(ctx, rank, world,
+ * id, id_bulk).  The first communicator carries the small exchanges on the ctx stream (64-byte MSM partials, commitments),
+ * the second the bulk polynomial broadcasts of a proof spread over several GPUs.
+ *   h2a_comm_allgather[_dev]: raw bytes, rank order (`recv` holds world * bytes_per_rank).
+ *   h2a_msm_g1_sharded: one MSM whose points are split into per-rank ranges (each rank passes ITS bases and scalars): the
+ *     64-byte affine partials are allgathered and summed in rank order, so every rank returns the same bytes.
+ *   h2a_circuit_set_distribution(ctx, circuit, rank, world, NULL, NULL) on a ctx with a communicator spreads ONE proof over
+ *     the ranks: commitments column-parallel, the transforms of a column on the rank that owns it (coefficient and extended
+ *     forms broadcast from there), the quotient row-parallel (slices allgathered).  All ranks must be given the same inputs
+ *     and all write the same proof bytes. */
+int h2a_comm_unique_id(uint8_t out_id[128]);
+int h2a_comm_init(h2a_ctx* ctx, int rank, int world, const uint8_t id[128], const uint8_t id_bulk[128]);
+int h2a_comm_destroy(h2a_ctx* ctx);
+int h2a_comm_rank(const h2a_ctx* ctx);
+int h2a_comm_world(const h2a_ctx* ctx);
+int h2a_comm_allgather(h2a_ctx* ctx, const uint8_t* send, uint8_t* recv, size_t bytes_per_rank);
+int h2a_comm_allgather_dev(h2a_ctx* ctx, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int h2a_comm_broadcast_dev(h2a_ctx* ctx, void* d_buf, size_t bytes, int root);
+int h2a_msm_g1_sharded(h2a_ctx* ctx, const h2a_bases* local_bases, size_t offset, const void* d_local_scalars, size_t n_local,
+                       uint8_t out_affine[64]);
+
 /* ---- Key generation: copy constraints -> sigma columns -------------------------------------
  * The permutation part of `keygen_vk` / `keygen_pk` (examples/simple-example.rs:593-594, :696-697).  An assembly
  * holds one permutation over the cells (col, row) of the n_cols permutation columns (`vk.permutation`,

@@ -31,5 +31,5 @@ def one(src):
 with ThreadPoolExecutor(8) as ex:
     objs = list(ex.map(one, b.SOURCES))
 out = os.path.join(out_dir, "libh2agg_%s.so" % name)
-subprocess.check_call([b.NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"])
+subprocess.check_call([b.NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"])
 print(out)

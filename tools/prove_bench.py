@@ -140,8 +140,11 @@ def run(ctx, args):
     circ.set_keys(g, gl, fixed_b, sigmas_b, fr(ctx, [0xC0FFEE]), fr(ctx, [7]))
     t_keys = time.perf_counter() - t0
     world = getattr(args, "world", 1)
-    if world > 1:   # column-parallel commitments: every rank proves the same inputs and commits its share
-        circ.set_distribution(args.rank, world, device="cuda")
+    if world > 1:   # every rank proves the same inputs; see Circuit.set_distribution for what is shared
+        if getattr(args, "native", True):
+            circ.set_distribution(args.rank, world, native=True)
+        else:
+            circ.set_distribution(args.rank, world, device="cuda")
     blinds = random_blinds(ctx, circ.blinds_len(), 3)
     try:        # witness columns in pinned host memory, as a caller that owns its buffers would arrange
         import torch
@@ -185,6 +188,7 @@ def main():
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--lookups", type=int, default=9)
+    ap.add_argument("--no-native", dest="native", action="store_false", help="several GPUs: share only the commitments, through a torch.distributed callback")
     ap.add_argument("--precompute", type=int, default=PROVER_TABLE_BITS, help="window bits of the per-Params MSM tables (0 = none, -1 = the library's choice for single MSMs)")
     args = ap.parse_args()
     args.rank, local_rank, args.world = (int(os.environ.get(v, d)) for v, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
@@ -195,22 +199,27 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = h2a.Context(local_rank)
+    if args.world > 1 and args.native:
+        ctx.comm_init_torch()
     res = run(ctx, args)
     res["n_gpus"] = args.world
     if args.world > 1:
         t = torch.tensor([res["value"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res["value"] = float(t[0])
+        res["proof_sha256"] = hashlib.sha256(res["proof_digest_src"]).hexdigest()
         digest = torch.tensor(list(hashlib.sha256(res.pop("proof_digest_src")).digest()), dtype=torch.uint8, device="cuda")
         alld = [torch.empty_like(digest) for _ in range(args.world)]
         dist.all_gather(alld, digest)
         res["proofs_identical_across_ranks"] = all(bool((d == alld[0]).all()) for d in alld)
-        res["config"]["distribution"] = "commitments column-parallel over %d GPUs (64-byte results allgathered with NCCL); everything else replicated" % args.world
+        res["config"]["distribution"] = ("commitments and transforms column-parallel over %d GPUs (results allgathered / broadcast by the library's own NCCL communicators), "
+                                         "quotient row-parallel; lookup permutations, grand products, evaluations and openings replicated" % args.world) if args.native else \
+            "commitments column-parallel over %d GPUs (64-byte results allgathered through torch.distributed); everything else replicated" % args.world
     else:
         import hashlib
         res["proof_sha256"] = hashlib.sha256(res.pop("proof_digest_src")).hexdigest()
     if args.rank == 0:
-        print(json.dumps(res), flush=True)
+        print(json.dumps({k: v for k, v in res.items() if not k.startswith("_")}), flush=True)
     if args.world > 1:
         dist.barrier()
         dist.destroy_process_group()
