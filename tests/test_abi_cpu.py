@@ -1,6 +1,7 @@
 """CPU-only checks of the C-ABI library: it loads, exports every symbol include/h2agg.h declares,
 refuses to run without a GPU (no fallback), and its host-side glue (transcript, point sums, roots of
 unity) agrees with the oracle.  No device compute here."""
+import os
 import random
 
 import numpy as np
@@ -177,3 +178,70 @@ def test_tree_halves_never_share_a_region():
     bad = (ctypes.c_int64 * 6)()
     assert lib.h2a_tree_layout(ctypes.c_uint64(96), 5, 0, 0, bad) == -1    # not a multiple of 2^(R+1)
     assert lib.h2a_tree_layout(ctypes.c_uint64(64), 5, 0, 5, bad) == -1    # round out of range
+
+
+# ---- the boundary as other languages see it: the Rust crates and a plain C program
+def _run_tool(*args):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return subprocess.run([sys.executable] + [os.path.join(root, a) if a.endswith(".py") else a for a in args], capture_output=True, text=True, cwd=root)
+
+
+def test_rust_sys_crate_matches_header():
+    """h2agg-sys/src/lib.rs is generated from include/h2agg.h: the committed file is current, and it declares exactly the
+    functions the header declares (which test_every_declared_symbol_is_exported ties to the built library)."""
+    import re
+    r = _run_tool("tools/gen_rust_sys.py", "--check")
+    assert r.returncode == 0, r.stdout + r.stderr
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "h2agg-sys", "src", "lib.rs")).read()
+    in_crate = sorted(set(re.findall(r"pub fn (h2a_[a-z0-9_]+)\(", text)))
+    assert in_crate == h2a.declared_symbols()
+    for opaque in ("h2a_ctx", "h2a_bases", "h2a_circuit", "h2a_assembly", "h2a_transcript"):
+        assert "pub struct %s" % opaque in text
+    assert "pub type h2a_exchange_fn" in text and "pub const H2A_ERR_PROOF: c_int = -5;" in text
+
+
+def test_rust_shim_uses_only_declared_symbols():
+    """Every sys::h2a_* the safe wrappers call exists in the header, and the wrappers cover the reference's surface
+    (best_multiexp, best_fft, EvaluationDomain, Params read / write / verifier_params, create_proof, verify_proof)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "h2agg-shim", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(h2a_[a-z0-9_]+)\(", text))
+    assert used and used <= set(h2a.declared_symbols()), used - set(h2a.declared_symbols())
+    for name in ("pub fn best_multiexp", "pub fn best_fft", "pub struct EvaluationDomain", "pub fn lagrange_to_coeff", "pub fn coeff_to_extended",
+                 "pub fn extended_to_coeff", "pub fn setup", "pub fn read", "pub fn write", "pub fn verifier_params", "pub fn commit_lagrange",
+                 "pub fn create_proof", "pub fn verify_proof", "pub fn verify_accumulate", "pub struct Transcript"):
+        assert name in text, name
+
+
+def test_header_is_valid_c_and_smoke_program_compiles(tmp_path):
+    """include/h2agg.h is C, not just C++: the plain C smoke program compiles and links against the built library (it runs
+    on the GPU box, tests/test_gpu_abi_c.py); its known answers are current with the oracle's big-integer model."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = _run_tool("tools/gen_abi_smoke_kat.py", "--check")
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = str(tmp_path / "abi_smoke")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"),
+                        "-L" + os.path.dirname(h2a.library_path()), "-lh2agg", "-Wl,-rpath," + os.path.dirname(h2a.library_path()), "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_generated_field_square_is_current_and_checked():
+    """csrc/field_mul_gen.cuh is what tools/gen_field_mul.py emits, and the generator's op lists still pass their check
+    against Python big integers (random and edge operands, no carry dropped)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_field_mul", os.path.join(root, "tools", "gen_field_mul.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    assert g.check(n_random=300)
+    parts = [g.HEADER]
+    for field, p_int in (("0", g.FQ), ("1", g.FR)):
+        parts.append(g.emit(g.build("sqr", p_int), "mont_sqr_wide", "sqr", field))
+    parts.append("}  // namespace h2a\n")
+    assert open(g.OUT).read() == "\n\n".join(parts)
