@@ -156,12 +156,15 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = h2a.Context(local_rank)
+    if world > 1:
+        ctx.comm_init_torch()     # the library's own NCCL communicators (csrc/comm.cu); torch.distributed only carries the unique ids
     ctx.set_profiling(True)
     n = 1 << args.log_n
     cpu_threads = max(1, orc.hw_threads() // world)     # all ranks check at once
 
     def combine(partial):
-        return h2a.allgather_sum(partial, device="cuda") if world > 1 else partial
+        # 64-byte affine partials allgathered as raw bytes by the library (h2a_comm_allgather) and summed in rank order
+        return h2a.g1_sum(ctx.comm_allgather(partial)) if world > 1 else partial
 
     def barrier():
         if world > 1:

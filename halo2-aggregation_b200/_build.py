@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libh2agg.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["misc.cu", "msm.cu", "ntt.cu", "abi.cu", "glue.cu", "plonk_verify.cu", "plonk_prove.cu", "keygen.cu", "params.cu", "comm.cu"]
+SOURCES = ["misc.cu", "msm.cu", "ntt.cu", "abi.cu", "glue.cu", "plonk_verify.cu", "plonk_prove.cu", "keygen.cu", "params.cu", "comm.cu", "mulvar.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

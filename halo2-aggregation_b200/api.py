@@ -61,6 +61,7 @@ def load_library():
     lib.h2a_launch_count.restype = ctypes.c_uint64
     lib.h2a_bases_len.restype = c_sz
     lib.h2a_blinds_len.restype = c_sz
+    lib.h2a_mulvar_witness_len.restype = c_sz
     lib.h2a_proof_len.restype = c_sz
     lib.h2a_prove_phase_name.restype = ctypes.c_char_p
     lib.h2a_transcript_new.restype = ctypes.c_void_p
@@ -236,6 +237,33 @@ class Context:
         h = ctypes.c_void_p()
         self._check(self.lib.h2a_params_verifier_view(self.h, g_lagrange.h, c_sz(public_inputs_size), ctypes.byref(h)))
         return Bases(self, h)
+
+    # ---- aggregation-circuit witness generation (row f4)
+    def mulvar_witness_len(self):
+        return int(self.lib.h2a_mulvar_witness_len())
+
+    def mulvar_witness(self, points, scalars, aux, want_witness=True):
+        """Witness cells of m non-native mul_var (csrc/mulvar.cu): (results m*64, witness m*len*32 or None, status u32[m]).
+        Raises H2AError when an entry cannot be witnessed; `e.status` then holds the per-entry status."""
+        points, scalars, aux = _bytes(points), _bytes(scalars), _bytes(aux)
+        m = points.size // 64
+        if scalars.size != 32 * m or aux.size != 64:
+            raise ValueError("mulvar_witness: m points of 64 bytes, m scalars of 32 bytes, one auxiliary point")
+        res = np.zeros(64 * m, np.uint8)
+        wit = np.zeros(32 * self.mulvar_witness_len() * m, np.uint8) if want_witness else None
+        status = np.zeros(m, np.uint32)
+        rc = self.lib.h2a_mulvar_witness(self.h, _ptr(points), _ptr(scalars), c_sz(m), _ptr(aux), _ptr(res), _ptr(wit), _ptr(status))
+        if rc != 0:
+            err = H2AError(rc, self.lib.h2a_last_error(self.h).decode())
+            err.status = status
+            raise err
+        return res, wit, status
+
+    def mulvar_witness_dev(self, d_points, d_scalars, m, aux, d_results, d_witness):
+        status = np.zeros(m, np.uint32)
+        self._check(self.lib.h2a_mulvar_witness_dev(self.h, ctypes.c_void_p(d_points), ctypes.c_void_p(d_scalars), c_sz(m), _ptr(_bytes(aux)),
+                                                   ctypes.c_void_p(d_results), ctypes.c_void_p(d_witness), _ptr(status)))
+        return status
 
     # ---- several GPUs (the library's own NCCL plumbing, csrc/comm.cu)
     def comm_init(self, rank, world, ids):

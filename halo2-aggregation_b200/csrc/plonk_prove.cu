@@ -712,7 +712,7 @@ int to_ext(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* coef, uint8_t* ext) {
 // to_coef + to_ext of a group of columns on the transform lane, ordered after everything queued on the ctx stream so far
 // (the columns' last writes).  tmp_n[3] / tmp_m are the lane's work buffers: nothing else touches them during a proof.
 // Without the lane (H2A_PROVE_NTT_OVERLAP=0) the same transforms are queued on the ctx stream itself.
-int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& cols) {
+int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& cols, const std::vector<int>* owners = nullptr) {
     ProverState* p = c->prover;
     if (cols.empty()) return H2A_OK;
     // several GPUs: column q of this proof's running count is transformed by rank q % world only, and its coefficient and
@@ -720,8 +720,8 @@ int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& c
     const bool dist = native_dist(ctx, c);
     const int W = c->dist_world, me = c->dist_rank;
     std::vector<int> owner(cols.size(), me);
-    if (dist) for (size_t j = 0; j < cols.size(); j++) owner[j] = (int)((p->dist_cols_done + j) % (size_t)W);
-    p->dist_cols_done += cols.size();
+    if (dist) for (size_t j = 0; j < cols.size(); j++) owner[j] = owners ? (*owners)[j] : (int)((p->dist_cols_done + j) % (size_t)W);
+    if (!owners) p->dist_cols_done += cols.size();
     const uint32_t n = c->shape.n, m = 1u << c->shape.ext_k;
     auto run = [&](cudaStream_t lane) -> int {
         for (size_t j = 0; j < cols.size(); j++)
@@ -766,8 +766,9 @@ int commit(h2a_ctx* ctx, const h2a_bases* bases, const uint8_t* d_scalars, uint3
 // (host_src, optional: column j is still in host memory there and is copied into cols[j] on the way, overlapped with the
 // previous column's MSM)
 int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, const std::vector<const uint8_t*>& cols, uint32_t n,
-                 std::vector<hh::PointA>& out, const std::vector<const uint8_t*>* host_src = nullptr) {
+                 std::vector<hh::PointA>& out, const std::vector<const uint8_t*>* host_src = nullptr, const std::vector<int>* owners = nullptr) {
     std::vector<uint8_t> pts(64 * cols.size(), 0);
+    auto owner_of = [&](size_t j) { return owners ? (*owners)[j] : (int)(j % (size_t)c->dist_world); };   // column j is committed by this rank
     if (c->dist_world > 1 && (c->dist_exchange || h2a_comm_active(ctx))) {   // this rank's share of the columns, then the exchange
         if (host_src)   // every rank needs every column on its device later: copy them all first
             for (size_t j = 0; j < cols.size(); j++)
@@ -775,7 +776,7 @@ int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, con
         std::vector<const uint8_t*> mine;
         std::vector<size_t> idx;
         for (size_t j = 0; j < cols.size(); j++)
-            if ((int)(j % (size_t)c->dist_world) == c->dist_rank) { mine.push_back(cols[j]); idx.push_back(j); }
+            if (owner_of(j) == c->dist_rank) { mine.push_back(cols[j]); idx.push_back(j); }
         std::vector<size_t> ns(mine.size(), n);
         std::vector<uint8_t> part(64 * mine.size() + 64);
         if (!mine.empty()) H2A_TRY(h2a_msm_batch_dev(ctx, bases, mine.data(), ns.data(), (int)mine.size(), part.data()));
@@ -787,7 +788,7 @@ int commit_batch(h2a_ctx* ctx, const h2a_circuit* c, const h2a_bases* bases, con
             std::vector<uint8_t> all(pts.size() * (size_t)c->dist_world);
             H2A_TRY(h2a_comm_allgather(ctx, pts.data(), all.data(), pts.size()));
             for (size_t j = 0; j < cols.size(); j++)
-                memcpy(pts.data() + 64 * j, all.data() + pts.size() * (j % (size_t)c->dist_world) + 64 * j, 64);
+                memcpy(pts.data() + 64 * j, all.data() + pts.size() * (size_t)owner_of(j) + 64 * j, 64);
         }
     } else {
         std::vector<size_t> ns(cols.size(), n);
@@ -1196,8 +1197,17 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     hh::Fr theta = tr.squeeze();                                                   // :378
     H2A_TRY(upload_fr(ctx, slot(S_THETA), theta));
 
+    // several GPUs (native distribution): lookup li belongs to rank li % world from its permutation to its grand product —
+    // only the owner sorts it, commits A', S', Z and transforms them; the other ranks receive the commitments and the
+    // coefficient / extended forms.  Permutation chunks are computed everywhere (cheap) and committed round-robin.
+    const bool dist = native_dist(ctx, c);
+    const int dist_me = c->dist_rank, dist_w = dist ? c->dist_world : 1;
+    auto lk_owner = [&](size_t li) { return dist ? (int)(li % (size_t)dist_w) : dist_me; };
+    auto pz_owner = [&](size_t ci) { return dist ? (int)((ci + 1 + s.lookups.size()) % (size_t)dist_w) : dist_me; };
+    uint32_t lookup_err = 0;                                                       // 1 + index of a lookup whose input is not in its table
     for (size_t li = 0; li < s.lookups.size(); li++) {                             // :380-387, src/lookup.rs:49-79
         ProverState::Lk& l = p->lk[li];
+        if (lk_owner(li) != dist_me) { bl += 64ull * (n - u) + 32ull * bf; continue; }
         LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_in_first[li], p->qargs.lk_in_cnt[li], slot(S_THETA), n, l.A);
         LAUNCH1D(dev::compress_kernel, n, 128, p->d_tab_n, p->qargs.lk_tab_first[li], p->qargs.lk_tab_cnt[li], slot(S_THETA), n, l.S);
         {   // A' and S' on the device: sort both, match runs to table entries, hand out the left-overs
@@ -1218,8 +1228,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
             uint32_t host_counters[4];
             H2A_CUDA(ctx, cudaMemcpyAsync(host_counters, counters, 16, cudaMemcpyDeviceToHost, st));
             H2A_CUDA(ctx, cudaStreamSynchronize(st));
-            if (host_counters[2] || host_counters[0] != host_counters[1])
-                H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: lookup %zu has an input value absent from its table", li);
+            if ((host_counters[2] || host_counters[0] != host_counters[1]) && !lookup_err) lookup_err = (uint32_t)li + 1;
         }
         H2A_CUDA(ctx, cudaMemcpyAsync(l.pa.lag + 32ull * u, bl, 32ull * (n - u), cudaMemcpyHostToDevice, st));
         bl += 32ull * (n - u);
@@ -1227,16 +1236,24 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         bl += 32ull * (n - u);
         bl += 32ull * bf;  // this lookup's Z tail, consumed after beta and gamma
     }
+    if (dist && !s.lookups.empty()) {   // every rank must learn of a failed lookup before any of them enters the next collective
+        std::vector<uint8_t> all(4 * (size_t)dist_w);
+        H2A_TRY(h2a_comm_allgather(ctx, (const uint8_t*)&lookup_err, all.data(), 4));
+        for (int r = 0; r < dist_w && !lookup_err; r++) memcpy(&lookup_err, all.data() + 4 * r, 4);
+    }
+    if (lookup_err) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: lookup %u has an input value absent from its table", lookup_err - 1);
     if (!s.lookups.empty()) {
+        std::vector<int> owners;
+        for (size_t li = 0; li < s.lookups.size(); li++) { owners.push_back(lk_owner(li)); owners.push_back(lk_owner(li)); }
         {
             std::vector<Poly3*> tcols;
             for (auto& l : p->lk) { tcols.push_back(&l.pa); tcols.push_back(&l.ps); }
-            H2A_TRY(transform_columns(ctx, c, tcols));
+            H2A_TRY(transform_columns(ctx, c, tcols, dist ? &owners : nullptr));
         }
         std::vector<const uint8_t*> cols;
         for (auto& l : p->lk) { cols.push_back(l.pa.lag); cols.push_back(l.ps.lag); }
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms, nullptr, dist ? &owners : nullptr));
         H2A_TRY(write_points(cms, "permuted lookup column"));
     }
     steps.mark("lookup permuted columns");
@@ -1285,6 +1302,7 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     steps.mark("permutation grand products");
     for (size_t li = 0; li < s.lookups.size(); li++) {                             // :411-417, src/lookup.rs:81-106
         ProverState::Lk& l = p->lk[li];
+        if (lk_owner(li) != dist_me) continue;
         LAUNCH1D(dev::lookup_terms_kernel, n, 128, l.A, l.S, l.pa.lag, l.ps.lag, slot(S_BETA), slot(S_GAMMA), u, n, p->tmp_n[0], p->tmp_n[1]);
         LAUNCH1D(dev::batch_inverse_kernel, (n + dev::INV_CHUNK - 1) / dev::INV_CHUNK, 128, p->tmp_n[1], n);
         LAUNCH1D(dev::mul_arrays_kernel, n, 256, p->tmp_n[0], p->tmp_n[1], n, p->tmp_n[2]);
@@ -1294,17 +1312,21 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         H2A_CUDA(ctx, cudaMemcpyAsync(l.z.lag + 32ull * (n - bf), bl_lookup_z[li], 32ull * bf, cudaMemcpyHostToDevice, st));
     }
     {
-        std::vector<Poly3*> tcols;
-        for (auto& q : p->pz) tcols.push_back(&q);
-        for (auto& l : p->lk) tcols.push_back(&l.z);
-        H2A_TRY(transform_columns(ctx, c, tcols));
-    }
-    {   // permutation Z (:402-409) then lookup Z (:411-417) commitments, one batch
+        std::vector<int> owners;
+        for (size_t ci = 0; ci < p->pz.size(); ci++) owners.push_back(pz_owner(ci));
+        for (size_t li = 0; li < p->lk.size(); li++) owners.push_back(lk_owner(li));
+        {
+            std::vector<Poly3*> tcols;
+            for (auto& q : p->pz) tcols.push_back(&q);
+            for (auto& l : p->lk) tcols.push_back(&l.z);
+            H2A_TRY(transform_columns(ctx, c, tcols, dist ? &owners : nullptr));
+        }
+        // permutation Z (:402-409) then lookup Z (:411-417) commitments, one batch
         std::vector<const uint8_t*> cols;
         for (auto& q : p->pz) cols.push_back(q.lag);
         for (auto& l : p->lk) cols.push_back(l.z.lag);
         std::vector<hh::PointA> cms;
-        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms));
+        H2A_TRY(commit_batch(ctx, c, p->g_lagrange, cols, n, cms, nullptr, dist ? &owners : nullptr));
         H2A_TRY(write_points(cms, "grand product"));
     }
     steps.mark("lookup grand products + Z commitments");

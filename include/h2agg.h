@@ -286,6 +286,25 @@ int h2a_params_verifier_view(h2a_ctx* ctx, const h2a_bases* g_lagrange, size_t p
 int h2a_prove_phase_ms(h2a_ctx* ctx, const h2a_circuit* circuit, float* ms, int cap);
 const char* h2a_prove_phase_name(const h2a_ctx* ctx, int index);
 
+/* ---- aggregation-circuit witness generation: the non-native `mul_var` (row f4) ----------------------------
+ * `ecc_chip.mul_var(region, point, scalar, offset)` is how the in-circuit verifier multiplies G1 points by transcript
+ * scalars: src/multiopen.rs:393 (z_i W_i), :443 (Horner chain of commitments), :474,480,486 (W, ZW, F), :492 (E),
+ * src/vanishing.rs:181-187 (quotient pieces) — about 37 per aggregated proof.  The chip (halo2wrong, not in the tree) holds an Fq
+ * coordinate as 4 limbs of 68 bits in Fr cells (examples/simple-example.rs:396-397, packing as :535-548) and witnesses every Fq
+ * product a*b = q*p + r with limb products.  h2a_mulvar_witness fills those cells for m independent (point, scalar) pairs in one
+ * launch, one thread per pair: out_results[i] = scalars[i] * points[i] (affine) and h2a_mulvar_witness_len() Fr elements per
+ * pair in the layout documented in csrc/mulvar.cu (bits of the scalar, then per bit the records of one doubling and one
+ * addition, limbs of the intermediate points, a final correction by -(2^254 aux)).  `aux` is the auxiliary point the incomplete
+ * affine additions start from.  An entry whose ladder meets equal x coordinates (scalar 0, the identity as input, ...) cannot be
+ * witnessed: the call returns H2A_ERR_INVALID after filling status_out[i] (0 = ok) for every entry; status_out may be NULL.
+ * PARITY UNPINNED at the dependency boundary: the cell layout is this library's statement of the published algorithm; the
+ * values are checked against the big-integer oracle (oracle/mulvar.py). */
+size_t h2a_mulvar_witness_len(void);
+int h2a_mulvar_witness(h2a_ctx* ctx, const uint8_t* points /* m*64 */, const uint8_t* scalars /* m*32 */, size_t m, const uint8_t aux[64],
+                       uint8_t* out_results /* m*64 */, uint8_t* out_witness /* m*len*32, may be NULL */, uint32_t* status_out);
+int h2a_mulvar_witness_dev(h2a_ctx* ctx, const void* d_points, const void* d_scalars, size_t m, const uint8_t aux[64], void* d_results,
+                           void* d_witness, uint32_t* status_out);
+
 /* Blake2b transcript with Challenge255 (src/transcript.rs:58,72,105-107,122-124). */
 typedef struct h2a_transcript h2a_transcript;
 h2a_transcript* h2a_transcript_new(void);
