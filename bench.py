@@ -14,8 +14,12 @@ halo2 `best_multiexp` / `best_fft`) on the same inputs, at the benchmark's own s
 
 Next to the headline the line carries, each with its own roofline fractions and same-run CPU figure:
   `strong`   one fixed 2^22-point and one fixed 2^24-point MSM split over the N ranks (point ranges),
-  `ntt`      Fr NTT at k=22 and the k=20 -> 2^22 coset extension (N = 1 only: a transform does not shard),
-  `prove`    the k=20 prover pipeline at every N (column-parallel commitments + sharded transforms under torchrun),
+  `ntt`      Fr NTT at k=22 / k=24 and the k=20 -> 2^22 coset extension (N = 1 only: a transform does not shard),
+  `sweep`    the small end of BASELINE configs 2 and 3: MSM 2^16..2^20 and NTT k=16..20, each beside the oracle (N = 1),
+  `mulvar`   row f4: witness cells of the non-native mul_var of 64 aggregated proofs (N = 1),
+  `params`   row f3: the k=20 parameter file written and read back, both encodings (N = 1),
+  `prove`    the k=20 prover pipeline at every N (one proof spread over the ranks by the library's own NCCL plumbing:
+             commitments, lookups and transforms column-parallel, quotient row-parallel),
   `batch`    64 proofs proved + verify-accumulated, one share per rank (BASELINE config 5),
   `e2e_cold` bases upload + window-table build + first MSM from host scalars.
 `--impl reference` times the CPU restatement of the reference's path (oracle/, halo2 `best_multiexp`)
@@ -331,7 +335,8 @@ def main():
     import bench_extras
     from oracle import plonk as pk        # the oracle's verifier: checker of the proofs the blocks below produce
     from oracle import pymodel as pm
-    env = dict(ctx=ctx, h2a=h2a, orc=orc, pk=pk, pm=pm, torch=torch, dist=dist, rank=rank, world=world, local_rank=local_rank, args=args,
+    from oracle import mulvar as mv       # checker of the witness cells of the mul_var block
+    env = dict(ctx=ctx, h2a=h2a, orc=orc, pk=pk, pm=pm, mv=mv, torch=torch, dist=dist, rank=rank, world=world, local_rank=local_rank, args=args,
                timed=timed, barrier=barrier, combine=combine, all_ranks_ok=all_ranks_ok, hbm_peak=hbm_peak, peak_src=peak_src,
                modmul_peak=modmul_peak, cpu_threads=cpu_threads)
     extras = {}
@@ -346,6 +351,9 @@ def main():
     if not args.no_extras:
         if world == 1:
             extras["ntt"] = bench_extras.ntt_block(env)
+            extras["sweep"] = bench_extras.sweep_block(env)
+            extras["mulvar"] = bench_extras.mulvar_block(env)
+            extras["params"] = bench_extras.params_block(env)
         extras["batch"] = bench_extras.batch_block(env)
     if not args.no_prove:
         extras["prove"] = bench_extras.prove_block(env)

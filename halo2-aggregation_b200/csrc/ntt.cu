@@ -30,7 +30,14 @@ struct NttTables {
 
 namespace {
 
-constexpr int NTT_THREADS = 256;
+constexpr int NTT_THREADS = 256;   // upper bound; a launch uses one thread per register group of the tile
+// butterfly levels a register group takes at once (2: radix-4 groups, 4 elements per thread; 3: radix-8, 8 elements)
+#ifndef NTT_NB
+#define NTT_NB 2
+#endif
+#ifndef NTT_MINB
+#define NTT_MINB 3
+#endif
 constexpr int LOG_PW_LO = 10;
 
 struct PassArgs {
@@ -51,22 +58,30 @@ struct PassArgs {
     uint32_t s1, s2;       // radix bits of passes 1 and 2 (last pass only; 0 when absent)
 };
 
-// shared-memory element storage: two planes of uint4 so that consecutive elements are 16 B apart
-struct SmemView {
+// shared-memory element storage: two planes of uint4 so that consecutive elements are 16 B apart.  SWZ: the low three
+// bits of the index are XORed with the next three, so that the strided accesses of the register groups below (8 lanes of a
+// quarter-warp reading elements 4 or 8 apart) still fall into eight different 16-byte bank groups.
+template <bool SWZ>
+struct SmemViewT {
     uint4* lo;
     uint4* hi;
-    __device__ __forceinline__ Fr get(uint32_t i) const {
+    __device__ __forceinline__ static uint32_t at(uint32_t i) { return SWZ ? i ^ ((i >> 3) & 7u) : i; }
+    __device__ __forceinline__ Fr get(uint32_t i_) const {
+        const uint32_t i = at(i_);
         Fr r;
         uint4 a = lo[i], b = hi[i];
         r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
         r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
         return r;
     }
-    __device__ __forceinline__ void put(uint32_t i, const Fr& v) const {
+    __device__ __forceinline__ void put(uint32_t i_, const Fr& v) const {
+        const uint32_t i = at(i_);
         lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
         hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
     }
 };
+typedef SmemViewT<true> SmemView;      // data tile
+typedef SmemViewT<false> TwView;       // twiddle table
 
 __device__ __forceinline__ Fr tw_lookup(const PassArgs& a, uint32_t e) {  // omega^(+-e), e < n
     uint32_t n_mask = (1u << a.log_n) - 1u;
@@ -86,51 +101,78 @@ __device__ __forceinline__ Fr load_input(const PassArgs& a, uint32_t gidx) {
     return v;
 }
 
-// radix-2 DIF stages over `rows` sub-transforms of 2^s points held in shared memory.
+// DIF stages lh = b + NB - 1 .. b of `rows` sub-transforms of 2^s points held in shared memory, NB stages at a time IN
+// REGISTERS: a thread takes the 2^NB elements of one row whose digits differ in bits [b, b + NB), runs the NB butterfly levels
+// on them without touching shared memory, and puts them back — one shared-memory round trip and one barrier per NB levels
+// instead of per level, and the index arithmetic of a work item is shared by NB * 2^(NB-1) butterflies.
 // Element (row t, digit d) lives at d*dstride + t*tstride.  Output digit i ends at position bitrev_s(i).
-__device__ __forceinline__ void smem_dif(const SmemView& sm, const SmemView& ltw, uint32_t s, uint32_t log_rows,
-                                         uint32_t dstride, uint32_t tstride, bool rows_fastest) {
-    const uint32_t half_n = 1u << (s - 1);
-    const uint32_t total = half_n << log_rows;  // butterflies per stage
-    for (uint32_t lh = s; lh-- > 0;) {          // h = 2^lh
-        const uint32_t h = 1u << lh;
-        for (uint32_t b = threadIdx.x; b < total; b += NTT_THREADS) {
-            uint32_t t, q;
-            if (rows_fastest) { t = b & ((1u << log_rows) - 1u); q = b >> log_rows; }
-            else { q = b & (half_n - 1u); t = b >> (s - 1); }
-            uint32_t pos = q & (h - 1u);
-            uint32_t d0 = ((q >> lh) << (lh + 1)) + pos;
-            uint32_t i0 = d0 * dstride + t * tstride, i1 = i0 + h * dstride;
-            Fr u = sm.get(i0), v = sm.get(i1);
-            sm.put(i0, u + v);
-            Fr d = u - v;
-            if (pos) d = d * ltw.get(pos << (s - 1 - lh));
-            sm.put(i1, d);
+template <int NB>
+__device__ __forceinline__ void reg_group(const SmemView& sm, const TwView& ltw, uint32_t s, uint32_t b, uint32_t log_rows,
+                                          uint32_t dstride, uint32_t tstride, bool rows_fastest) {
+    constexpr uint32_t E = 1u << NB;
+    const uint32_t log_q = s - NB;                       // digits left to the work item index
+    const uint32_t items = 1u << (log_q + log_rows);
+    for (uint32_t w = threadIdx.x; w < items; w += blockDim.x) {
+        uint32_t t, q;
+        if (rows_fastest) { t = w & ((1u << log_rows) - 1u); q = w >> log_rows; }
+        else { q = w & ((1u << log_q) - 1u); t = w >> log_q; }
+        const uint32_t q_lo = q & ((1u << b) - 1u);
+        const uint32_t d_base = ((q >> b) << (b + NB)) | q_lo;
+        const uint32_t i_base = d_base * dstride + t * tstride, i_step = dstride << b;
+        Fr v[E];
+#pragma unroll
+        for (uint32_t j = 0; j < E; j++) v[j] = sm.get(i_base + j * i_step);
+#pragma unroll
+        for (int st = NB - 1; st >= 0; st--) {
+            const uint32_t half = 1u << st, lh = b + (uint32_t)st;
+#pragma unroll
+            for (uint32_t j0 = 0; j0 < E; j0++) {
+                if (j0 & half) continue;
+                const uint32_t j1 = j0 | half;
+                const uint32_t pos = q_lo | ((j0 & (half - 1u)) << b);     // digit of the pair below bit lh
+                const Fr u = v[j0], x = v[j1];
+                v[j0] = u + x;
+                Fr d = u - x;
+                if (pos) d = d * ltw.get(pos << (s - 1u - lh));
+                v[j1] = d;
+            }
         }
-        __syncthreads();
+#pragma unroll
+        for (uint32_t j = 0; j < E; j++) sm.put(i_base + j * i_step, v[j]);
     }
+    __syncthreads();
+}
+// all s levels, NTT_NB at a time from the top (the remainder comes last)
+__device__ __forceinline__ void smem_dif(const SmemView& sm, const TwView& ltw, uint32_t s, uint32_t log_rows,
+                                         uint32_t dstride, uint32_t tstride, bool rows_fastest) {
+    uint32_t top = s;                                    // levels [0, top) are still to do
+    while (top >= NTT_NB) { top -= NTT_NB; reg_group<NTT_NB>(sm, ltw, s, top, log_rows, dstride, tstride, rows_fastest); }
+#if NTT_NB == 3
+    if (top == 2) reg_group<2>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest);
+#endif
+    if (top == 1) reg_group<1>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest);
 }
 
-__device__ __forceinline__ void load_local_twiddles(const PassArgs& a, const SmemView& ltw) {
+__device__ __forceinline__ void load_local_twiddles(const PassArgs& a, const TwView& ltw) {
     // ltw[e] = omega_{n_p}^e = omega^(e * n / n_p), e < n_p/2
     const uint32_t half_n = 1u << (a.s - 1);
-    for (uint32_t e = threadIdx.x; e < half_n; e += NTT_THREADS) ltw.put(e, tw_lookup(a, e << (a.log_n - a.s)));
+    for (uint32_t e = threadIdx.x; e < half_n; e += blockDim.x) ltw.put(e, tw_lookup(a, e << (a.log_n - a.s)));
 }
 
 // Passes 1..P-1: the transformed digit has stride R = 2^log_r; a block takes `tile` consecutive inner
 // positions.  Shared layout: d * tile + t.
-__global__ void __launch_bounds__(NTT_THREADS) ntt_strided_pass_kernel(PassArgs a) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MINB) ntt_strided_pass_kernel(PassArgs a) {
     extern __shared__ uint4 smem_raw[];
     const uint32_t np = 1u << a.s, tile = 1u << a.log_tile, elems = np << a.log_tile;
     SmemView sm{smem_raw, smem_raw + elems};
-    SmemView ltw{smem_raw + 2 * elems, smem_raw + 2 * elems + (np >> 1)};
+    TwView ltw{smem_raw + 2 * elems, smem_raw + 2 * elems + (np >> 1)};
     const uint32_t tiles_per_outer = 1u << (a.log_r - a.log_tile);
     const uint32_t outer = blockIdx.x / tiles_per_outer;
     const uint32_t inner0 = (blockIdx.x % tiles_per_outer) << a.log_tile;
     const size_t base = ((size_t)outer << (a.s + a.log_r)) + inner0;
 
     load_local_twiddles(a, ltw);
-    for (uint32_t x = threadIdx.x; x < elems; x += NTT_THREADS) {
+    for (uint32_t x = threadIdx.x; x < elems; x += blockDim.x) {
         uint32_t d = x >> a.log_tile, t = x & (tile - 1u);
         sm.put(x, load_input(a, (uint32_t)(base + ((size_t)d << a.log_r) + t)));
     }
@@ -138,7 +180,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_strided_pass_kernel(PassArgs 
     smem_dif(sm, ltw, a.s, a.log_tile, tile, 1, true);
     // twist by omega_m^(i_p * inner), m = n_p * R, omega_m = omega^(n/m)
     const uint32_t log_m = a.s + a.log_r;
-    for (uint32_t x = threadIdx.x; x < elems; x += NTT_THREADS) {
+    for (uint32_t x = threadIdx.x; x < elems; x += blockDim.x) {
         uint32_t dpos = x >> a.log_tile, t = x & (tile - 1u);
         uint32_t ip = __brev(dpos) >> (32 - a.s);
         uint32_t inner = inner0 + t;
@@ -151,26 +193,26 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_strided_pass_kernel(PassArgs 
 
 // Last pass: contiguous 2^s-point sub-transforms; a block takes `tile` of them that differ in digit 1
 // so that the digit-reversed stores form runs of `tile` consecutive outputs.
-// Shared layout: t * (n_p + 1) + d  (one element of padding per row).
-__global__ void __launch_bounds__(NTT_THREADS) ntt_last_pass_kernel(PassArgs a) {
+// Shared layout: t * n_p + d (swizzled, see SmemViewT).
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MINB) ntt_last_pass_kernel(PassArgs a) {
     extern __shared__ uint4 smem_raw[];
-    const uint32_t np = 1u << a.s, tile = 1u << a.log_tile, row = np + 1u, elems = row << a.log_tile;
+    const uint32_t np = 1u << a.s, tile = 1u << a.log_tile, row = np, elems = row << a.log_tile;
     SmemView sm{smem_raw, smem_raw + elems};
-    SmemView ltw{smem_raw + 2 * elems, smem_raw + 2 * elems + (np >> 1)};
+    TwView ltw{smem_raw + 2 * elems, smem_raw + 2 * elems + (np >> 1)};
     const uint32_t log_outer = a.log_n - a.s;             // number of sub-transforms = 2^log_outer
     const uint32_t log_rest = log_outer - a.s1;           // digits between digit 1 and the last one
     const uint32_t i_rest = blockIdx.x & ((1u << log_rest) - 1u);
     const uint32_t i1_0 = (blockIdx.x >> log_rest) << a.log_tile;
 
     load_local_twiddles(a, ltw);
-    for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += NTT_THREADS) {
+    for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += blockDim.x) {
         uint32_t t = x >> a.s, d = x & (np - 1u);
         uint32_t outer = ((i1_0 + t) << log_rest) + i_rest;
         sm.put(t * row + d, load_input(a, (outer << a.s) + d));
     }
     __syncthreads();
     smem_dif(sm, ltw, a.s, a.log_tile, 1, row, false);
-    for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += NTT_THREADS) {
+    for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += blockDim.x) {
         uint32_t t = x & (tile - 1u), dpos = x >> a.log_tile;
         uint32_t ip = a.s ? (__brev(dpos) >> (32 - a.s)) : 0u;
         // output index: i_1 + n_1 * i_2 + (n / n_P) * i_P   (i_rest is digit 2 when there are 3 passes)
@@ -283,8 +325,10 @@ void split_bits(uint32_t k, uint32_t s[3], int* passes) {
     else { s[0] = (k + 2) / 3; s[1] = (k + 1) / 3; s[2] = k / 3; *passes = 3; }
 }
 
+// one thread per register group of the tile, whole warps, at most NTT_THREADS
+unsigned threads_for(uint32_t log_elems) { return (unsigned)std::min<uint32_t>(NTT_THREADS, std::max<uint32_t>(32u, (1u << log_elems) >> NTT_NB)); }
 size_t smem_bytes_strided(uint32_t s, uint32_t log_tile) { return 32ull * ((1u << (s + log_tile)) + (1u << (s ? s - 1 : 0))); }
-size_t smem_bytes_last(uint32_t s, uint32_t log_tile) { return 32ull * ((((1u << s) + 1u) << log_tile) + (1u << (s ? s - 1 : 0))); }
+size_t smem_bytes_last(uint32_t s, uint32_t log_tile) { return 32ull * ((1u << (s + log_tile)) + (1u << (s ? s - 1 : 0))); }
 
 }  // namespace
 
@@ -352,7 +396,7 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
             a.dst = d_work;
             a.log_tile = std::min(log_tile_max, a.log_r);
             size_t sh = smem_bytes_strided(a.s, a.log_tile);
-            ntt_strided_pass_kernel<<<n >> (a.s + a.log_tile), NTT_THREADS, sh, ctx->stream>>>(a);
+            ntt_strided_pass_kernel<<<n >> (a.s + a.log_tile), threads_for(a.s + a.log_tile), sh, ctx->stream>>>(a);
         } else {
             a.dst = d_dst;
             a.s1 = passes >= 2 ? s[0] : 0;
@@ -364,7 +408,7 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
                 a.pw_hi = a.pw_lo + (32ull << LOG_PW_LO);
             }
             size_t sh = smem_bytes_last(a.s, a.log_tile);
-            ntt_last_pass_kernel<<<n >> (a.s + a.log_tile), NTT_THREADS, sh, ctx->stream>>>(a);
+            ntt_last_pass_kernel<<<n >> (a.s + a.log_tile), threads_for(a.s + a.log_tile), sh, ctx->stream>>>(a);
         }
         H2A_LAUNCH_CHECK(ctx);
         h2a_prof_mark(ctx);

@@ -181,6 +181,128 @@ def _oracle_accepts(env, chk):
     return pk.pairing_relation_holds(res, chk["secret"]), res
 
 
+def sweep_block(env):
+    """BASELINE configs 2 and 3 below the sizes the other blocks cover: G1 MSM 2^16..2^20 and Fr NTT k = 16..20, inputs resident
+    in HBM, each checked against the oracle and timed beside it (the 2^22 / 2^24 points of both sweeps are `strong` and `ntt`)."""
+    ctx, h2a, orc, torch = env["ctx"], env["h2a"], env["orc"], env["torch"]
+    out = {"msm": {}, "ntt": {}}
+    for log_n in (16, 18, 20):
+        n = 1 << log_n
+        d_b = torch.empty(64 * n, dtype=torch.uint8, device="cuda")
+        d_s = torch.empty(32 * n, dtype=torch.uint8, device="cuda")
+        ctx.gen_bases_dev(21, n, d_b.data_ptr())
+        ctx.gen_scalars_dev(22, n, d_s.data_ptr())
+        hb = ctx.bases_from_device(d_b.data_ptr(), n)
+        if not env["args"].no_precompute:
+            hb.precompute(-1)
+        step = lambda: ctx.msm_dev(hb, d_s.data_ptr(), n)
+        for _ in range(3):
+            step()
+        ms, _, _, _, got = env["timed"](step, 10)
+        t0 = time.perf_counter()
+        want = orc.msm(d_b.cpu().numpy(), d_s.cpu().numpy(), threads=env["cpu_threads"])
+        cpu_s = time.perf_counter() - t0
+        if bytes(got) != bytes(want):
+            raise SystemExit("bench.py: PARITY FAILURE — MSM sweep 2^%d differs from the oracle" % log_n)
+        out["msm"]["2^%d" % log_n] = {"ms": ms / 10, "value": n / (ms / 10 * 1e-3) / 1e6, "unit": "Mpts/s", "parity_checked": "oracle",
+                                      "cpu_baseline": {"value": n / cpu_s / 1e6, "unit": "Mpts/s", "cores": env["cpu_threads"], "kind": "port",
+                                                       "sample": "one best_multiexp over the same points, %.3f s" % cpu_s}}
+        hb.free()
+        del d_b, d_s
+    for k in (16, 18, 20):
+        n = 1 << k
+        d_in = torch.empty(32 * n, dtype=torch.uint8, device="cuda")
+        d_out = torch.empty(32 * n, dtype=torch.uint8, device="cuda")
+        ctx.gen_scalars_dev(23, n, d_in.data_ptr())
+        omega = h2a.fr_root_of_unity(k)
+        phases = []
+        for it in range(8):
+            d_out.copy_(d_in)
+            torch.cuda.current_stream().synchronize()
+            ctx.ntt_dev(d_out.data_ptr(), k, omega)
+            if it >= 3:
+                phases.append(ctx.last_phases(1))
+        kernel_ms = sum(sum(ms for _, ms in ph) for ph in phases) / len(phases)
+        host_in = d_in.cpu().numpy()
+        t0 = time.perf_counter()
+        want = orc.fft(host_in, k, omega)
+        cpu_s = time.perf_counter() - t0
+        if bytes(d_out.cpu().numpy()) != bytes(want):
+            raise SystemExit("bench.py: PARITY FAILURE — NTT sweep k=%d differs from the oracle" % k)
+        out["ntt"]["k=%d" % k] = {"kernel_ms": kernel_ms, "value": n / (kernel_ms * 1e-3) / 1e6, "unit": "Melements/s", "parity_checked": "oracle",
+                                  "cpu_baseline": {"value": n / cpu_s / 1e6, "unit": "Melements/s", "cores": env["cpu_threads"], "kind": "port",
+                                                   "sample": "one best_fft of the same input, %.3f s" % cpu_s}}
+        del d_in, d_out
+    torch.cuda.empty_cache()
+    return out
+
+
+def mulvar_block(env):
+    """Row f4: witness cells of the non-native mul_var of 64 aggregated proofs (37 each) in one launch, three entries checked
+    cell for cell against the oracle (env["mv"]), which is also timed beside it."""
+    ctx, pm, mv, torch = env["ctx"], env["pm"], env["mv"], env["torch"]
+    m = 37 * 64
+    ln = ctx.mulvar_witness_len()
+    aux_pt = pm.g1_mul(pm.G1, 0xabcdef123457)
+    aux = np.frombuffer(pm.affine_bytes(aux_pt), dtype=np.uint8)
+    d_p = torch.empty(64 * m, dtype=torch.uint8, device="cuda")
+    d_s = torch.empty(32 * m, dtype=torch.uint8, device="cuda")
+    d_r = torch.empty(64 * m, dtype=torch.uint8, device="cuda")
+    d_w = torch.empty(32 * ln * m, dtype=torch.uint8, device="cuda")
+    ctx.gen_bases_dev(31, m, d_p.data_ptr())
+    ctx.gen_scalars_dev(32, m, d_s.data_ptr())
+    best = None
+    for _ in range(3):
+        ctx.sync()
+        t0 = time.perf_counter()
+        ctx.mulvar_witness_dev(d_p.data_ptr(), d_s.data_ptr(), m, aux, d_r.data_ptr(), d_w.data_ptr())
+        ctx.sync()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    pts, scal, res = d_p.cpu().numpy(), d_s.cpu().numpy(), d_r.cpu().numpy()
+    t_cpu = 0.0
+    for i in (0, m // 2, m - 1):
+        t0 = time.perf_counter()
+        q, cells, st = mv.mulvar_witness(pm.affine_from_bytes(bytes(pts[64 * i:64 * i + 64])), pm.fr_from_mont_bytes(bytes(scal[32 * i:32 * i + 32])), aux_pt)
+        t_cpu += time.perf_counter() - t0
+        got = d_w[32 * ln * i:32 * ln * (i + 1)].cpu().numpy()
+        if st != 0 or bytes(got) != b"".join(pm.fr_mont_bytes(c) for c in cells) or pm.affine_from_bytes(bytes(res[64 * i:64 * i + 64])) != q:
+            raise SystemExit("bench.py: PARITY FAILURE — mul_var witness cells differ from the oracle (entry %d)" % i)
+    del d_p, d_s, d_r, d_w
+    torch.cuda.empty_cache()
+    return {"metric": "mul_var witness generation, 64 proofs x 37 mul_var", "value": best, "unit": "s", "higher_is_better": False, "mul_var": m,
+            "cells_per_mul_var": ln, "witness_bytes": 32 * ln * m, "write_gb_per_s": 32 * ln * m / best / 1e9,
+            "parity_checked": "oracle (oracle/mulvar.py), 3 entries cell for cell; PARITY UNPINNED at the dependency boundary (halo2wrong's cell layout is not in the reference)",
+            "cpu_baseline": {"value": t_cpu / 3 * m, "unit": "s", "cores": 1, "kind": "port",
+                             "sample": "3 mul_var on the Python big-integer oracle (%.3f s each) scaled to %d; compiled BigUint code would be one to two orders faster" % (t_cpu / 3, m)}}
+
+
+def params_block(env):
+    """Row f3: the k=20 parameters written to and read back from a parameter file (both encodings), points compared."""
+    import tempfile
+    ctx = env["ctx"]
+    import prove_bench
+    k = 20
+    g, gl = ctx.kzg_setup(k, prove_bench.fr(ctx, [0x1234567]))
+    out = {"k": k}
+    ref = g.download()
+    with tempfile.TemporaryDirectory() as td:
+        for compressed in (False, True):
+            path = os.path.join(td, "halo2-%d.params" % k)
+            t0 = time.perf_counter(); ctx.params_write(path, k, g, gl, compressed=compressed); tw = time.perf_counter() - t0
+            size = os.path.getsize(path)
+            t0 = time.perf_counter(); k2, g2, gl2, _ = ctx.params_read(path); tr = time.perf_counter() - t0
+            if k2 != k or bytes(g2.download()) != bytes(ref):
+                raise SystemExit("bench.py: parameter file round trip changed the points")
+            g2.free(); gl2.free()
+            os.remove(path)
+            out["compressed" if compressed else "in_memory_form"] = {"file_bytes": size, "write_s": tw, "read_s": tr,
+                                                                     "read_gb_per_s": size / tr / 1e9}
+    g.free(); gl.free()
+    out["note"] = "read = file -> pinned staging -> HBM with the Blake2b digest and the on-curve check of every point (square roots when compressed)"
+    return out
+
+
 def prove_block(env):
     """`agg-circuit prove s at k=20`: the prover pipeline at every N, the proof checked by the oracle's verifier."""
     import prove_bench

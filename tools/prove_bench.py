@@ -160,6 +160,12 @@ def run(ctx, args):
         proof, inst = circ.prove(inst_b, adv_b, blinds)
         times.append(time.perf_counter() - t0)
     phases = circ.prove_phases()
+    try:        # device memory in use with everything of this proof resident (params, tables, proving key, workspaces)
+        import torch
+        free_b, total_b = torch.cuda.mem_get_info()
+        hbm_used_gb = (total_b - free_b) / 1e9
+    except Exception:
+        hbm_used_gb = None
     # validity: (e, f, w, zw) from the verifier glue must satisfy s*W == ZW + F + E
     efwzw = circ.verify(inst, proof)
     e, f, w, zw = (efwzw[64 * i:64 * i + 64] for i in range(4))
@@ -179,7 +185,7 @@ def run(ctx, args):
                                             "aggregation circuit do), so their commitments see mostly-zero windows; the permuted, grand-product, quotient "
                                             "and opening polynomials are full-width field elements",
                                  "msm_tables": args.precompute},
-                      "phases_ms": dict(phases), "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof),
+                      "phases_ms": dict(phases), "hbm_used_gb": hbm_used_gb, "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof),
                       "op_counts": op_counts(shape), "_check": check, "_efwzw": efwzw})
 
 
@@ -188,6 +194,7 @@ def main():
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--lookups", type=int, default=9)
+    ap.add_argument("--oracle-check", action="store_true", help="also replay the proof through the oracle's verifier (test infrastructure)")
     ap.add_argument("--no-native", dest="native", action="store_false", help="several GPUs: share only the commitments, through a torch.distributed callback")
     ap.add_argument("--precompute", type=int, default=PROVER_TABLE_BITS, help="window bits of the per-Params MSM tables (0 = none, -1 = the library's choice for single MSMs)")
     args = ap.parse_args()
@@ -218,6 +225,13 @@ def main():
     else:
         import hashlib
         res["proof_sha256"] = hashlib.sha256(res.pop("proof_digest_src")).hexdigest()
+    if args.rank == 0 and args.oracle_check:   # the oracle's verifier (oracle/plonk.py) replays the proof: O(proof size), any k
+        import bench_extras
+        from oracle import loader as orc, plonk as pk, pymodel as pm
+        orc.load()
+        ok, _ = bench_extras._oracle_accepts(dict(pk=pk, pm=pm), res["_check"])
+        res["parity_checked"] = "oracle verifier (oracle/plonk.py verify_proof + pairing relation)" if ok else "ORACLE VERIFIER REJECTS THE PROOF"
+        res["proof_verifies"] = res["proof_verifies"] and ok
     if args.rank == 0:
         print(json.dumps({k: v for k, v in res.items() if not k.startswith("_")}), flush=True)
     if args.world > 1:
