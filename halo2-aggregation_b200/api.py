@@ -283,6 +283,12 @@ class Context:
         self.comm_init(rank, world, np.frombuffer(ids[0], dtype=np.uint8))
         return rank, world
 
+    def comm_traffic(self):
+        """(bytes sent, bytes received) by this rank through the library's collectives so far."""
+        out = (ctypes.c_uint64 * 2)()
+        self._check(self.lib.h2a_comm_traffic(self.h, out))
+        return int(out[0]), int(out[1])
+
     def comm_destroy(self):
         self._check(self.lib.h2a_comm_destroy(self.h))
 

@@ -26,6 +26,8 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -55,12 +57,14 @@ NcclApi& nccl() {
     BIND(CommDestroy, "ncclCommDestroy");
     BIND(AllGather, "ncclAllGather");
     BIND(Broadcast, "ncclBroadcast");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
     BIND(GroupStart, "ncclGroupStart");
     BIND(GroupEnd, "ncclGroupEnd");
     BIND(GetErrorString, "ncclGetErrorString");
     BIND(GetLastError, "ncclGetLastError");
 #undef BIND
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GroupStart && api.GroupEnd &&
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.Send && api.Recv && api.GroupStart && api.GroupEnd &&
              api.GetErrorString;
     return api;
 }
@@ -88,11 +92,25 @@ int h2a_comm_group_end(h2a_ctx* ctx) {
 int h2a_comm_broadcast_on(h2a_ctx* ctx, int lane, void* d_buf, size_t bytes, int root, cudaStream_t stream) {
     if (!h2a_comm_active(ctx)) H2A_FAIL(ctx, H2A_ERR_INVALID, "broadcast: no communicator (h2a_comm_init)");
     H2A_NCCL(ctx, nccl().Broadcast(d_buf, d_buf, bytes, ncclUint8, root, (ncclComm_t)ctx->comm[lane], stream));
+    ctx->comm_bytes[root == ctx->comm_rank ? 0 : 1] += bytes;
+    return H2A_OK;
+}
+// point-to-point pieces of an exchange (inside h2a_comm_group_start / _end; both sides enumerate their pieces in the same order)
+int h2a_comm_send_on(h2a_ctx* ctx, int lane, const void* d_buf, size_t bytes, int peer, cudaStream_t stream) {
+    H2A_NCCL(ctx, nccl().Send(d_buf, bytes, ncclUint8, peer, (ncclComm_t)ctx->comm[lane], stream));
+    ctx->comm_bytes[0] += bytes;
+    return H2A_OK;
+}
+int h2a_comm_recv_on(h2a_ctx* ctx, int lane, void* d_buf, size_t bytes, int peer, cudaStream_t stream) {
+    H2A_NCCL(ctx, nccl().Recv(d_buf, bytes, ncclUint8, peer, (ncclComm_t)ctx->comm[lane], stream));
+    ctx->comm_bytes[1] += bytes;
     return H2A_OK;
 }
 int h2a_comm_allgather_on(h2a_ctx* ctx, int lane, const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t stream) {
     if (!h2a_comm_active(ctx)) H2A_FAIL(ctx, H2A_ERR_INVALID, "allgather: no communicator (h2a_comm_init)");
     H2A_NCCL(ctx, nccl().AllGather(d_send, d_recv, bytes_per_rank, ncclUint8, (ncclComm_t)ctx->comm[lane], stream));
+    ctx->comm_bytes[0] += bytes_per_rank;
+    ctx->comm_bytes[1] += bytes_per_rank * (size_t)(ctx->comm_world - 1);
     return H2A_OK;
 }
 
@@ -141,6 +159,12 @@ int h2a_comm_destroy(h2a_ctx* ctx) {
     return H2A_OK;
 }
 
+int h2a_comm_traffic(const h2a_ctx* ctx, uint64_t out_sent_received[2]) {
+    if (!ctx || !out_sent_received) return H2A_ERR_INVALID;
+    out_sent_received[0] = ctx->comm_bytes[0];
+    out_sent_received[1] = ctx->comm_bytes[1];
+    return H2A_OK;
+}
 int h2a_comm_rank(const h2a_ctx* ctx) { return ctx ? ctx->comm_rank : 0; }
 int h2a_comm_world(const h2a_ctx* ctx) { return ctx ? ctx->comm_world : 1; }
 

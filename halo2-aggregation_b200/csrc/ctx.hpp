@@ -25,6 +25,9 @@ struct h2a_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;       // second stream of this lane (the two halves of the affine tree)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream_lo[2] = {nullptr, nullptr};   // one priority level below: the tree's backward passes (msm_tree_prio)
+    cudaEvent_t ev_tree[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int msm_tree_prio = 0;                // 1: backward passes of the addition tree on lower-priority streams (H2A_MSM_TREE_PRIO)
     int stream_priority = 0;              // priority both streams are created with (the device's greatest)
     std::string err;
     uint64_t launches = 0;
@@ -67,6 +70,7 @@ struct h2a_ctx {
     // prover's transform lane), this process's rank, and a staging buffer for host-buffer collectives
     void* comm[2] = {nullptr, nullptr};
     int comm_rank = 0, comm_world = 1;
+    uint64_t comm_bytes[2] = {0, 0};      // payload bytes this rank has put into / taken out of collectives since comm_init
     DevBuf comm_buf;
 
     // NTT workspace
@@ -147,4 +151,6 @@ bool h2a_comm_active(const h2a_ctx* ctx);
 int h2a_comm_group_start(h2a_ctx* ctx);
 int h2a_comm_group_end(h2a_ctx* ctx);
 int h2a_comm_broadcast_on(h2a_ctx* ctx, int lane, void* d_buf, size_t bytes, int root, cudaStream_t stream);
+int h2a_comm_send_on(h2a_ctx* ctx, int lane, const void* d_buf, size_t bytes, int peer, cudaStream_t stream);
+int h2a_comm_recv_on(h2a_ctx* ctx, int lane, void* d_buf, size_t bytes, int peer, cudaStream_t stream);
 int h2a_comm_allgather_on(h2a_ctx* ctx, int lane, const void* d_send, void* d_recv, size_t bytes_per_rank, cudaStream_t stream);

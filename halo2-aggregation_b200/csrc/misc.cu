@@ -258,6 +258,8 @@ int h2a_init(h2a_ctx** out, int device) {
     if (env && atoi(env) >= 1 && atoi(env) <= 64) ctx->msm_group_cols_host = atoi(env);
     env = getenv("H2A_MSM_ROUNDS_BIAS");
     if (env && atoi(env) >= -3 && atoi(env) <= 3) ctx->msm_rounds_bias = atoi(env);
+    env = getenv("H2A_MSM_TREE_PRIO");
+    if (env) ctx->msm_tree_prio = atoi(env) ? 1 : 0;
     env = getenv("H2A_MSM_ALGO");
     if (env) ctx->msm_algo = atoi(env) ? 1 : 0;
     *out = ctx;
@@ -283,6 +285,10 @@ int h2a_destroy(h2a_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (int h = 0; h < 2; h++) {
+        if (ctx->stream_lo[h]) cudaStreamDestroy(ctx->stream_lo[h]);
+        for (int e = 0; e < 2; e++) if (ctx->ev_tree[h][e]) cudaEventDestroy(ctx->ev_tree[h][e]);
+    }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->stream);

@@ -773,8 +773,19 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
         H2A_TRY(h2a_reserve(ctx, ctx->aff_scratch, 2 * (scratch_elems + totals_elems) * 32));
         // the second stream starts one phase late (after the first half's round-0 forward pass): the halves then run
         // out of step and each one's latency-bound inversion hides under the other's forward / backward kernel
+        // msm_tree_prio: the compute-bound backward passes go to a second, LOWER-priority stream per half, so that whenever a
+        // block slot frees up the block scheduler hands it to a pending forward-pass block (memory-latency-bound gathers,
+        // little arithmetic) first: the two kinds of blocks then share every SM instead of taking turns on the machine.
+        const bool split_prio = ctx->msm_tree_prio != 0;
+        if (split_prio && !ctx->stream_lo[0]) {
+            for (int h = 0; h < 2; h++) {
+                H2A_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream_lo[h], cudaStreamNonBlocking, ctx->stream_priority + 1));
+                for (int e = 0; e < 2; e++) H2A_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tree[h][e], cudaEventDisableTiming));
+            }
+        }
         for (int half = 0; half < 2; half++) {
             cudaStream_t hs = half ? ctx->stream2 : st;
+            cudaStream_t bs = split_prio ? ctx->stream_lo[half] : hs;               // stream of the backward passes
             uint8_t* scratch = (uint8_t*)ctx->aff_scratch.p + (size_t)half * (scratch_elems + totals_elems) * 32;
             uint8_t* totals = scratch + scratch_elems * 32;
             uint8_t* const arrays[3] = {(uint8_t*)ctx->aff_a.p, (uint8_t*)ctx->aff_b.p, (uint8_t*)ctx->aff_c.p};
@@ -796,9 +807,17 @@ int msm_launch_c(h2a_ctx* ctx, const uint8_t* d_bases, uint32_t stride, uint32_t
                 }
                 aff_invert_totals_kernel<<<(blocks * 128 / INV_T + 63) / 64, 64, 0, hs>>>(totals, blocks * 128);
                 H2A_LAUNCH_CHECK(ctx);
-                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, hs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
-                else aff_backward_kernel<false><<<blocks, 128, 0, hs>>>(nullptr, nullptr, pts_in, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
+                if (split_prio) {
+                    H2A_CUDA(ctx, cudaEventRecord(ctx->ev_tree[half][0], hs));
+                    H2A_CUDA(ctx, cudaStreamWaitEvent(bs, ctx->ev_tree[half][0], 0));
+                }
+                if (round == 0) aff_backward_kernel<true><<<blocks, 128, 0, bs>>>(d_bases, sorted + 2 * o0, nullptr, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
+                else aff_backward_kernel<false><<<blocks, 128, 0, bs>>>(nullptr, nullptr, pts_in, n_out, n_multi + 2, (uint32_t)o0, round, scratch, totals, pts_out);
                 H2A_LAUNCH_CHECK(ctx);
+                if (split_prio) {   // the next round's forward pass reads these sums (and reuses the scratch)
+                    H2A_CUDA(ctx, cudaEventRecord(ctx->ev_tree[half][1], bs));
+                    H2A_CUDA(ctx, cudaStreamWaitEvent(hs, ctx->ev_tree[half][1], 0));
+                }
                 n_out /= 2;
             }
         }

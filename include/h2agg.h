@@ -230,6 +230,9 @@ int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* circuit, int rank, i
 int h2a_comm_unique_id(uint8_t out_id[128]);
 int h2a_comm_init(h2a_ctx* ctx, int rank, int world, const uint8_t id[128], const uint8_t id_bulk[128]);
 int h2a_comm_destroy(h2a_ctx* ctx);
+/* Payload bytes this rank has contributed to / received from the library's collectives since h2a_comm_init (a broadcast
+ * counts once at its root and once at every receiver). */
+int h2a_comm_traffic(const h2a_ctx* ctx, uint64_t out_sent_received[2]);
 int h2a_comm_rank(const h2a_ctx* ctx);
 int h2a_comm_world(const h2a_ctx* ctx);
 int h2a_comm_allgather(h2a_ctx* ctx, const uint8_t* send, uint8_t* recv, size_t bytes_per_rank);

@@ -332,7 +332,11 @@ def prove_block(env):
            "parity_checked": "oracle verifier (oracle/plonk.py verify_proof + pairing relation)" + ("; byte-identical proof on every rank" if world > 1 else ""),
            "proof_bytes": pr["proof_bytes"], "phases_ms": pr["phases_ms"], "workload": pr["config"]["workload"],
            "msm_tables": pr["config"]["msm_tables"], "op_counts": pr["op_counts"],
-           "distribution": pr["config"].get("distribution", "single GPU")}
+           "distribution": "single GPU" if world == 1 else
+                           "one proof over %d GPUs through the library's NCCL communicators: commitments, lookups and transforms column-parallel "
+                           "(coefficient forms broadcast, extended forms sent as row windows), quotient row-parallel; permutation grand products, "
+                           "evaluations and openings replicated" % world,
+           "nvlink_traffic_this_rank": pr.get("nvlink_traffic_this_rank")}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # CPU figure: the MSM / FFT sequence of create_proof replayed with the oracle's best_multiexp / best_fft
         k = args.prove_k

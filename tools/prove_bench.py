@@ -154,11 +154,16 @@ def run(ctx, args):
     except Exception:
         pinned = False
     times = []
+    traffic = None
     for it in range(args.steps + 1):
         ctx.sync()
+        tr0 = ctx.comm_traffic() if world > 1 and getattr(args, "native", True) else None
         t0 = time.perf_counter()
         proof, inst = circ.prove(inst_b, adv_b, blinds)
         times.append(time.perf_counter() - t0)
+        if tr0 is not None:
+            tr1 = ctx.comm_traffic()
+            traffic = {"sent_bytes_per_proof": tr1[0] - tr0[0], "received_bytes_per_proof": tr1[1] - tr0[1]}
     phases = circ.prove_phases()
     try:        # device memory in use with everything of this proof resident (params, tables, proving key, workspaces)
         import torch
@@ -185,7 +190,7 @@ def run(ctx, args):
                                             "aggregation circuit do), so their commitments see mostly-zero windows; the permuted, grand-product, quotient "
                                             "and opening polynomials are full-width field elements",
                                  "msm_tables": args.precompute},
-                      "phases_ms": dict(phases), "hbm_used_gb": hbm_used_gb, "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof),
+                      "phases_ms": dict(phases), "nvlink_traffic_this_rank": traffic, "hbm_used_gb": hbm_used_gb, "kzg_setup_s": t_setup, "set_keys_s": t_keys, "proof_digest_src": bytes(proof),
                       "op_counts": op_counts(shape), "_check": check, "_efwzw": efwzw})
 
 
