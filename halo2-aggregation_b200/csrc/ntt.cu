@@ -56,6 +56,7 @@ struct PassArgs {
     const uint8_t* pw_lo;  // base^i (times a constant for post), i < 2^LOG_PW_LO
     const uint8_t* pw_hi;  // base^(i << LOG_PW_LO)
     uint32_t s1, s2;       // radix bits of passes 1 and 2 (last pass only; 0 when absent)
+    int bulk;              // last pass: rows staged by TMA bulk copies (see ntt_last_pass_kernel)
 };
 
 // shared-memory element storage: two planes of uint4 so that consecutive elements are 16 B apart.  SWZ: the low three
@@ -106,9 +107,11 @@ __device__ __forceinline__ Fr load_input(const PassArgs& a, uint32_t gidx) {
 // on them without touching shared memory, and puts them back — one shared-memory round trip and one barrier per NB levels
 // instead of per level, and the index arithmetic of a work item is shared by NB * 2^(NB-1) butterflies.
 // Element (row t, digit d) lives at d*dstride + t*tstride.  Output digit i ends at position bitrev_s(i).
+// `stage` (optional): the group's inputs are read from there — a linear array of 32-byte elements with the same logical indexing,
+// filled by TMA bulk copies (ntt_last_pass_kernel) — instead of from the planes; the results always go to the planes.
 template <int NB>
 __device__ __forceinline__ void reg_group(const SmemView& sm, const TwView& ltw, uint32_t s, uint32_t b, uint32_t log_rows,
-                                          uint32_t dstride, uint32_t tstride, bool rows_fastest) {
+                                          uint32_t dstride, uint32_t tstride, bool rows_fastest, const uint8_t* stage = nullptr) {
     constexpr uint32_t E = 1u << NB;
     const uint32_t log_q = s - NB;                       // digits left to the work item index
     const uint32_t items = 1u << (log_q + log_rows);
@@ -121,7 +124,7 @@ __device__ __forceinline__ void reg_group(const SmemView& sm, const TwView& ltw,
         const uint32_t i_base = d_base * dstride + t * tstride, i_step = dstride << b;
         Fr v[E];
 #pragma unroll
-        for (uint32_t j = 0; j < E; j++) v[j] = sm.get(i_base + j * i_step);
+        for (uint32_t j = 0; j < E; j++) v[j] = stage ? Fr::load(stage + 32u * (i_base + j * i_step)) : sm.get(i_base + j * i_step);
 #pragma unroll
         for (int st = NB - 1; st >= 0; st--) {
             const uint32_t half = 1u << st, lh = b + (uint32_t)st;
@@ -144,13 +147,13 @@ __device__ __forceinline__ void reg_group(const SmemView& sm, const TwView& ltw,
 }
 // all s levels, NTT_NB at a time from the top (the remainder comes last)
 __device__ __forceinline__ void smem_dif(const SmemView& sm, const TwView& ltw, uint32_t s, uint32_t log_rows,
-                                         uint32_t dstride, uint32_t tstride, bool rows_fastest) {
+                                         uint32_t dstride, uint32_t tstride, bool rows_fastest, const uint8_t* stage = nullptr) {
     uint32_t top = s;                                    // levels [0, top) are still to do
-    while (top >= NTT_NB) { top -= NTT_NB; reg_group<NTT_NB>(sm, ltw, s, top, log_rows, dstride, tstride, rows_fastest); }
+    while (top >= NTT_NB) { top -= NTT_NB; reg_group<NTT_NB>(sm, ltw, s, top, log_rows, dstride, tstride, rows_fastest, stage); stage = nullptr; }
 #if NTT_NB == 3
-    if (top == 2) reg_group<2>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest);
+    if (top == 2) { reg_group<2>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest, stage); stage = nullptr; }
 #endif
-    if (top == 1) reg_group<1>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest);
+    if (top == 1) reg_group<1>(sm, ltw, s, 0, log_rows, dstride, tstride, rows_fastest, stage);
 }
 
 __device__ __forceinline__ void load_local_twiddles(const PassArgs& a, const TwView& ltw) {
@@ -204,14 +207,43 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MINB) ntt_last_pass_kernel(Pa
     const uint32_t i_rest = blockIdx.x & ((1u << log_rest) - 1u);
     const uint32_t i1_0 = (blockIdx.x >> log_rest) << a.log_tile;
 
-    load_local_twiddles(a, ltw);
-    for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += blockDim.x) {
-        uint32_t t = x >> a.s, d = x & (np - 1u);
-        uint32_t outer = ((i1_0 + t) << log_rest) + i_rest;
-        sm.put(t * row + d, load_input(a, (outer << a.s) + d));
+    // The rows of this pass are contiguous in global memory (n_p elements = 32 n_p bytes each): when nothing has to happen to
+    // an element on its way in (no coset pre-scale, no zero padding) one elected thread asks the TMA unit for them — one 1-D bulk
+    // copy per row into a linear staging area, completion counted in bytes on an mbarrier — while the block builds its twiddle
+    // table; the first register group then reads its inputs from the staging area.  Otherwise every thread loads its elements.
+    uint8_t* stage = nullptr;
+    if (a.bulk) {
+        stage = (uint8_t*)(smem_raw + 2 * elems + 2 * (np >> 1) + 1);            // after the twiddle planes; 16-byte aligned
+        uint64_t* bar = (uint64_t*)(smem_raw + 2 * elems + 2 * (np >> 1));
+        const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar), row_bytes = 32u << a.s;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(row_bytes << a.log_tile) : "memory");
+            for (uint32_t t = 0; t < tile; t++) {
+                const uint32_t outer = ((i1_0 + t) << log_rest) + i_rest;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 (uint32_t)__cvta_generic_to_shared(stage + (size_t)t * row_bytes)),
+                             "l"(a.src + 32ull * ((size_t)outer << a.s)), "r"(row_bytes), "r"(bar_s)
+                             : "memory");
+            }
+        }
+        load_local_twiddles(a, ltw);
+        __syncthreads();                                                         // twiddles written, barrier initialised
+        uint32_t done;
+        do {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_s) : "memory");
+        } while (!done);
+    } else {
+        load_local_twiddles(a, ltw);
+        for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += blockDim.x) {
+            uint32_t t = x >> a.s, d = x & (np - 1u);
+            uint32_t outer = ((i1_0 + t) << log_rest) + i_rest;
+            sm.put(t * row + d, load_input(a, (outer << a.s) + d));
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    smem_dif(sm, ltw, a.s, a.log_tile, 1, row, false);
+    smem_dif(sm, ltw, a.s, a.log_tile, 1, row, false, stage);
     for (uint32_t x = threadIdx.x; x < (np << a.log_tile); x += blockDim.x) {
         uint32_t t = x & (tile - 1u), dpos = x >> a.log_tile;
         uint32_t ip = a.s ? (__brev(dpos) >> (32 - a.s)) : 0u;
@@ -407,7 +439,11 @@ int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_wo
                 a.pw_lo = (const uint8_t*)post->p;
                 a.pw_hi = a.pw_lo + (32ull << LOG_PW_LO);
             }
-            size_t sh = smem_bytes_last(a.s, a.log_tile);
+            // TMA staging needs whole rows that are read as they are: no pre-scale, no zero padding, rows of 1 to 16 KB (a 32 KB row is the
+            // whole tile: the staging area then halves the blocks per SM and the pass measured 4 % slower, k = 20)
+            static const bool bulk_on = !getenv("H2A_NTT_NO_BULK");
+            a.bulk = bulk_on && !a.pre_mode && a.n_in == n && a.s >= 5 && a.s <= 9;
+            size_t sh = smem_bytes_last(a.s, a.log_tile) + (a.bulk ? 16 + (32ull << (a.s + a.log_tile)) : 0);
             ntt_last_pass_kernel<<<n >> (a.s + a.log_tile), threads_for(a.s + a.log_tile), sh, ctx->stream>>>(a);
         }
         H2A_LAUNCH_CHECK(ctx);
