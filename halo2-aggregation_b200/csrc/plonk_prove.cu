@@ -1455,20 +1455,30 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
     if ((size_t)S_POINT0 + point_slot.size() > 1024) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: %zu evaluations and %zu rotations exceed the scalar buffer", evs.size(), point_slot.size());
     for (auto& kv : point_slot) H2A_TRY(upload_fr(ctx, slot(kv.second), rotate_point(s, x, kv.first)));
     {
-        std::vector<dev::EvalReq> reqs(evs.size());
-        for (size_t i = 0; i < evs.size(); i++) reqs[i] = dev::EvalReq{evs[i].coef, slot(point_slot[evs[i].rot]), slot(S_EVAL0 + (int)i)};
+        // several GPUs: evaluation i is computed by rank i % world (every rank holds every coefficient form); the 32-byte results
+        // are exchanged below
+        std::vector<dev::EvalReq> reqs;
+        for (size_t i = 0; i < evs.size(); i++)
+            if (!dist || (int)(i % (size_t)dist_w) == dist_me) reqs.push_back(dev::EvalReq{evs[i].coef, slot(point_slot[evs[i].rot]), slot(S_EVAL0 + (int)i)});
         H2A_CUDA(ctx, cudaMemcpyAsync(p->d_reqs, reqs.data(), sizeof(dev::EvalReq) * reqs.size(), cudaMemcpyHostToDevice, st));
         H2A_CUDA(ctx, cudaStreamSynchronize(st));   // reqs is a stack-owned vector
         const uint32_t nch = (n + dev::HORNER_L - 1) / dev::HORNER_L;
-        dim3 grid((nch + 127) / 128, (unsigned)reqs.size());
-        dev::chunk_values_multi_kernel<<<grid, 128, 0, st>>>(p->d_reqs, n, nch, p->eval_chunks);
-        H2A_LAUNCH_CHECK(ctx);
-        dev::fold_chunks_multi_kernel<<<(unsigned)reqs.size(), 256, 0, st>>>(p->d_reqs, nch, p->eval_chunks);
-        H2A_LAUNCH_CHECK(ctx);
+        if (!reqs.empty()) {
+            dim3 grid((nch + 127) / 128, (unsigned)reqs.size());
+            dev::chunk_values_multi_kernel<<<grid, 128, 0, st>>>(p->d_reqs, n, nch, p->eval_chunks);
+            H2A_LAUNCH_CHECK(ctx);
+            dev::fold_chunks_multi_kernel<<<(unsigned)reqs.size(), 256, 0, st>>>(p->d_reqs, nch, p->eval_chunks);
+            H2A_LAUNCH_CHECK(ctx);
+        }
     }
     std::vector<uint8_t> evb(32 * evs.size());
     H2A_CUDA(ctx, cudaMemcpyAsync(evb.data(), slot(S_EVAL0), evb.size(), cudaMemcpyDeviceToHost, st));
     H2A_CUDA(ctx, cudaStreamSynchronize(st));
+    if (dist) {   // slot i of rank i % world is the one that was computed
+        std::vector<uint8_t> all(evb.size() * (size_t)dist_w);
+        H2A_TRY(h2a_comm_allgather(ctx, evb.data(), all.data(), evb.size()));
+        for (size_t i = 0; i < evs.size(); i++) memcpy(evb.data() + 32 * i, all.data() + evb.size() * (i % (size_t)dist_w) + 32 * i, 32);
+    }
     std::vector<hh::Fr> evals(evs.size());
     for (size_t i = 0; i < evs.size(); i++) { evals[i] = hh::fr_load(evb.data() + 32 * i); write_scalar(evals[i]); }   // :438-510
     steps.mark("evaluations");
@@ -1505,8 +1515,6 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
         size_t used = 0;
         for (auto& kv : sets) {
             uint8_t* batch = p->tmp_n[1];
-            bool first = true;
-            for (size_t qi : kv.second) { LAUNCH1D(dev::axpy_kernel, n, 256, batch, mq[qi].coef, slot(S_V), n, first ? 1 : 0); first = false; }
             if (!point_slot.count(kv.first)) H2A_FAIL(ctx, H2A_ERR_INVALID, "create_proof: rotation without evaluation point");
             const uint8_t* d_z = slot(point_slot[kv.first]);
             if (used == slots) {                                                   // more rotation sets than slots: flush
@@ -1516,12 +1524,18 @@ int h2a_create_proof(h2a_ctx* ctx, h2a_circuit* c, const uint8_t* instance_cols,
                 wcols.clear();
                 used = 0;
             }
+            // several GPUs: the rotation set in position j of a batch of commitments belongs to rank j % world (the owner
+            // commit_batch gives column j): only that rank folds the set's polynomials and divides
+            const bool mine = !dist || (int)(used % (size_t)dist_w) == dist_me;
             uint8_t* q = p->h_ext + 32ull * n * used++;
+            wcols.push_back(q);
+            if (!mine) continue;
+            bool first = true;
+            for (size_t qi : kv.second) { LAUNCH1D(dev::axpy_kernel, n, 256, batch, mq[qi].coef, slot(S_V), n, first ? 1 : 0); first = false; }
             LAUNCH1D(dev::chunk_values_kernel, nchunks, 128, batch, n, d_z, p->chunks);
             dev::kate_carry_kernel<<<1, 128, 0, st>>>(p->chunks, nchunks, d_z, p->carries);
             H2A_LAUNCH_CHECK(ctx);
             LAUNCH1D(dev::kate_quotient_kernel, nchunks, 128, batch, n, d_z, p->carries, q);
-            wcols.push_back(q);
         }
         std::vector<hh::PointA> part;
         H2A_TRY(commit_batch(ctx, c, p->g, wcols, n, part));
