@@ -137,7 +137,11 @@ int h2a_comm_init(h2a_ctx* ctx, int rank, int world, const uint8_t id[128], cons
         ncclUniqueId uid;
         memcpy(&uid, ids[lane], 128);
         ncclComm_t comm = nullptr;
-        H2A_NCCL(ctx, nccl().CommInitRank(&comm, world, uid, rank));
+        const ncclResult_t r = nccl().CommInitRank(&comm, world, uid, rank);
+        if (r != ncclSuccess) {   // never leave a ctx with one communicator of the two
+            if (ctx->comm[0]) { nccl().CommDestroy((ncclComm_t)ctx->comm[0]); ctx->comm[0] = nullptr; }
+            H2A_FAIL(ctx, H2A_ERR_CUDA, "comm_init: ncclCommInitRank (communicator %d) -> %s", lane, nccl().GetErrorString(r));
+        }
         ctx->comm[lane] = comm;
     }
     ctx->comm_rank = rank;

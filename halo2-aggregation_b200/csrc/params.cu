@@ -145,9 +145,17 @@ const char PERSONAL[16] = {'H', '2', 'A', '-', 'P', 'a', 'r', 'a', 'm', 's', '-'
 
 extern "C" {
 
+static int params_write_impl(h2a_ctx* ctx, const char* path, uint32_t k, const h2a_bases* g, const h2a_bases* g_lagrange, int compressed,
+                             const uint8_t* trailer128);
 int h2a_params_write(h2a_ctx* ctx, const char* path, uint32_t k, const h2a_bases* g, const h2a_bases* g_lagrange, int compressed,
                      const uint8_t* trailer128) {
     H2A_DEVICE(ctx);
+    const int rc = params_write_impl(ctx, path, k, g, g_lagrange, compressed, trailer128);
+    if (rc != H2A_OK && path && ctx && ctx->err.find("cannot create") == std::string::npos) remove(path);   // no truncated file is left behind
+    return rc;
+}
+static int params_write_impl(h2a_ctx* ctx, const char* path, uint32_t k, const h2a_bases* g, const h2a_bases* g_lagrange, int compressed,
+                             const uint8_t* trailer128) {
     if (!ctx || !path || !g || !g_lagrange) return H2A_ERR_INVALID;
     if (k < 1 || k > 26) H2A_FAIL(ctx, H2A_ERR_INVALID, "params_write: k=%u not in 1..26", k);
     const uint64_t n = 1ull << k;

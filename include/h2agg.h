@@ -226,7 +226,9 @@ int h2a_circuit_set_distribution(h2a_ctx* ctx, h2a_circuit* circuit, int rank, i
  *   h2a_circuit_set_distribution(ctx, circuit, rank, world, NULL, NULL) on a ctx with a communicator spreads ONE proof over
  *     the ranks: commitments column-parallel, the transforms of a column on the rank that owns it (coefficient and extended
  *     forms broadcast from there), the quotient row-parallel (slices allgathered).  All ranks must be given the same inputs
- *     and all write the same proof bytes. */
+ *     and all write the same proof bytes.  A witness error every rank can see (a lookup input outside its table) fails on every
+ *     rank; a rank that fails for a reason of its own (a CUDA error, an allocation) leaves the others waiting in their next
+ *     collective, as in any NCCL program: abort the job. */
 int h2a_comm_unique_id(uint8_t out_id[128]);
 int h2a_comm_init(h2a_ctx* ctx, int rank, int world, const uint8_t id[128], const uint8_t id_bulk[128]);
 int h2a_comm_destroy(h2a_ctx* ctx);
