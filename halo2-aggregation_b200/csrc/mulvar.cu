@@ -7,7 +7,8 @@
 // represents an Fq coordinate as 4 limbs of 68 bits held in Fr cells (examples/simple-example.rs:396-397; the same packing as
 // the public inputs, :535-548) and constrains every Fq product a*b = q*p + r through limb products.  Filling those cells is
 // sequential big-integer code on the CPU in the reference and the Amdahl term of proving the aggregation circuit; here
-// one thread walks one mul_var and a launch covers every (proof, mul_var) pair of a batch.
+// a launch pair covers every (proof, mul_var) pair of a batch: one thread per mul_var walks the ladder and shares its
+// inversions, one thread per (mul_var, step) writes the records.
 //
 // PARITY UNPINNED: halo2wrong's exact cell layout is not visible from the reference, so the layout below is this library's
 // statement of that published algorithm (integer chip with a negative wrong modulus, incomplete affine addition with an
@@ -25,6 +26,7 @@
 //     v_1 = (t_2 + 2^68 t_3 - r_2 - 2^68 r_3 + v_0) / 2^136   (both exact: a*b + q*p' - r = 0 mod 2^272)
 // A step whose addition meets equal x coordinates (s = 0, P = +-AUX multiples, ...) cannot be witnessed with the incomplete
 // formulas — the circuit would be unsatisfiable — and is reported per entry.
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -109,17 +111,47 @@ __device__ void mul_low256(const uint32_t* x, const uint32_t* y, uint32_t* out) 
     for (int i = 0; i < 8; i++) out[i] = r[i];
 }
 
-// an integer below 2^192 as an Fr element in Montgomery form
-__device__ __forceinline__ void store_small(uint8_t* dst, const uint32_t* words, int n) {
-    Fr v = Fr::zero();
-    for (int i = 0; i < n; i++) v.l[i] = words[i];
-    v.to_mont().store(dst);
+// A small integer (NW 32-bit words) as an Fr element in Montgomery form: v * R mod r.  A full Montgomery product by R^2 costs 136
+// wide multiplications whatever the operand; with the word-serial product run over the NW words of v only — v * X / 2^(32 NW) mod r with
+// the constant X = R * 2^(32 NW) mod r — it costs 17 per word, and 22 of the 26 products of a record are such conversions.  The result
+// stays below 2r (checked over random and all-ones operands in Python), so one conditional subtraction finishes it.
+__constant__ uint32_t TO_MONT_X[3][8] = {
+    {0x15b8b9dau, 0x93e78865u, 0xb05ea154u, 0x16df2426u, 0x302ab839u, 0x1271b743u, 0xec6c226eu, 0x06bc037eu},     // NW = 1
+    {0xaf8b5a7au, 0x54c81065u, 0x97aa45f6u, 0x2b82a1efu, 0x330a5a6du, 0xbe492693u, 0x8229aff4u, 0x1847e486u},     // NW = 3
+    {0xebb7ae00u, 0xee881bd8u, 0x483e9406u, 0x076add9cu, 0x184bf72du, 0xe590c2b8u, 0xff54fbf4u, 0x1df79fc3u}};    // NW = 5
+template <int NW>
+__device__ __forceinline__ void store_small(uint8_t* dst, const uint32_t* words) {
+    static_assert(NW == 1 || NW == 3 || NW == 5, "constants exist for 1, 3 and 5 words");
+    constexpr int XI = NW == 1 ? 0 : NW == 3 ? 1 : 2;
+    uint32_t acc[10];
+#pragma unroll
+    for (int j = 0; j < 10; j++) acc[j] = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c += (uint64_t)words[i] * TO_MONT_X[XI][j] + acc[j]; acc[j] = (uint32_t)c; c >>= 32; }
+        c += acc[8]; acc[8] = (uint32_t)c; acc[9] += (uint32_t)(c >> 32);
+        const uint32_t m = acc[0] * FieldConst<FR>::INV;
+        c = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c += (uint64_t)m * FieldConst<FR>::mod(j) + acc[j]; acc[j] = (uint32_t)c; c >>= 32; }
+        c += acc[8]; acc[8] = (uint32_t)c; acc[9] += (uint32_t)(c >> 32);
+#pragma unroll
+        for (int j = 0; j < 9; j++) acc[j] = acc[j + 1];
+        acc[9] = 0;
+    }
+    Fr v;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v.l[j] = acc[j];
+    Fr::reduce_once(v.l);
+    v.store(dst);
 }
 __device__ void store_limbs(uint8_t* dst, const Fq& canonical) {   // 4 cells
     for (int i = 0; i < 4; i++) {
         uint32_t l[3];
         limb_of(canonical.l, i, l);
-        store_small(dst + 32 * i, l, 3);
+        store_small<3>(dst + 32 * i, l);
     }
 }
 
@@ -138,10 +170,10 @@ __device__ __noinline__ Fq nn_record(uint8_t* dst, const Fq& a_m, const Fq& b_m)
     uint32_t al[4][3], bl[4][3], ql[4][3], rl[4][3];
     for (int i = 0; i < 4; i++) { limb_of(a.l, i, al[i]); limb_of(b.l, i, bl[i]); limb_of(q, i, ql[i]); limb_of(r.l, i, rl[i]); }
     for (int i = 0; i < 4; i++) {
-        store_small(dst + 32 * i, al[i], 3);
-        store_small(dst + 32 * (4 + i), bl[i], 3);
-        store_small(dst + 32 * (8 + i), ql[i], 3);
-        store_small(dst + 32 * (12 + i), rl[i], 3);
+        store_small<3>(dst + 32 * i, al[i]);
+        store_small<3>(dst + 32 * (4 + i), bl[i]);
+        store_small<3>(dst + 32 * (8 + i), ql[i]);
+        store_small<3>(dst + 32 * (12 + i), rl[i]);
     }
     W8 t[4];
     for (int k = 0; k < 4; k++) {
@@ -151,7 +183,7 @@ __device__ __noinline__ Fq nn_record(uint8_t* dst, const Fq& a_m, const Fq& b_m)
             w8_add(t[k], limb_mul(al[i], bl[k - i]));
             w8_add(t[k], limb_mul(ql[i], np));
         }
-        store_small(dst + 32 * (16 + k), t[k].w, 6);
+        store_small<5>(dst + 32 * (16 + k), t[k].w);              // t_k < 2^141
     }
     W8 v = w8_zero();
     for (int half = 0; half < 2; half++) {
@@ -163,7 +195,7 @@ __device__ __noinline__ Fq nn_record(uint8_t* dst, const Fq& a_m, const Fq& b_m)
         w8_add(rr, w8_shl68(r1));
         w8_sub(u, rr);
         v = w8_shr136(u);
-        store_small(dst + 32 * (20 + half), v.w, 4);
+        store_small<3>(dst + 32 * (20 + half), v.w);              // v < 2^74
     }
     return r_m;
 }
@@ -175,22 +207,21 @@ __device__ __forceinline__ void store_point(uint8_t* dst, const MvPoint& p) {
     store_limbs(dst + 128, p.y.from_mont());
 }
 
-// T = A + B with the incomplete formula, three records; false when the x coordinates are equal
-__device__ bool mv_add(uint8_t* dst, const MvPoint& a, const MvPoint& b, MvPoint& out) {
+// T = A + B with the incomplete formula, three records; inv_dx = 1 / (xB - xA) comes from the shared inversion
+__device__ void mv_add(uint8_t* dst, const MvPoint& a, const MvPoint& b, const Fq& inv_dx, MvPoint& out) {
     const Fq dx = b.x - a.x;
-    if (dx.is_zero()) return false;
-    const Fq lam = (b.y - a.y) * dx.inv();
+    const Fq lam = (b.y - a.y) * inv_dx;
     nn_record(dst, lam, dx);
     const Fq l2 = nn_record(dst + 32 * MV_REC, lam, lam);
     out.x = l2 - a.x - b.x;
     const Fq m = nn_record(dst + 64 * MV_REC, lam, a.x - out.x);
     out.y = m - a.y;
-    return true;
 }
-__device__ void mv_double(uint8_t* dst, const MvPoint& a, MvPoint& out) {
+// D = 2 A, four records; inv_2y = 1 / (2 yA)
+__device__ void mv_double(uint8_t* dst, const MvPoint& a, const Fq& inv_2y, MvPoint& out) {
     const Fq xx = nn_record(dst, a.x, a.x);
     const Fq y2 = a.y.dbl();
-    const Fq lam = (xx.dbl() + xx) * y2.inv();
+    const Fq lam = (xx.dbl() + xx) * inv_2y;
     nn_record(dst + 32 * MV_REC, lam, y2);
     const Fq l2 = nn_record(dst + 64 * MV_REC, lam, lam);
     out.x = l2 - a.x.dbl();
@@ -198,42 +229,136 @@ __device__ void mv_double(uint8_t* dst, const MvPoint& a, MvPoint& out) {
     out.y = m - a.y;
 }
 
-// one thread per mul_var; status[i] = 0 ok, 1 + step when an addition met equal x coordinates, 0xffffffff for an identity input
+// Per-entry scratch: the 2 * 254 + 1 points of the ladder (D_s, T_s for every step, then Q), 128 bytes each — XYZZ while the
+// ladder runs, then affine x || y in the first half and the denominator of the formula that produced... consumed the point in the
+// second — and one 32-byte prefix product per point for the two shared inversions.
+constexpr uint32_t MV_PTS = 2 * MV_BITS + 1;
+constexpr size_t MV_SCRATCH = (size_t)MV_PTS * (128 + 32);
+
+// in-place: vals[k] (stride bytes apart, count of them, none zero) <- 1 / vals[k]; prefix: count x 32 bytes of scratch
+__device__ void mv_batch_invert(uint8_t* vals, size_t stride, uint32_t count, uint8_t* prefix) {
+    Fq run = Fq::one();
+    for (uint32_t k = 0; k < count; k++) {
+        run.store(prefix + 32ull * k);
+        run = run * Fq::load(vals + stride * k);
+    }
+    Fq inv = run.inv();
+    for (uint32_t k = count; k-- > 0;) {
+        const Fq v = Fq::load(vals + stride * k);
+        (inv * Fq::load(prefix + 32ull * k)).store(vals + stride * k);
+        inv = inv * v;
+    }
+}
+
+// First kernel, one thread per mul_var; status[i] = 0 ok, 1 + step when an addition met equal x coordinates, 0xffffffff for an identity
+// input.  The ladder runs in XYZZ coordinates (no inversion), ONE shared inversion turns its 509 points into affine points, a second
+// one inverts the 509 denominators of the affine formulas (2y of every doubling, x2 - x1 of every addition): two field inversions per
+// mul_var instead of 509.  The records are written by the second kernel from what this one leaves in the scratch.
 __global__ void __launch_bounds__(32) mulvar_witness_kernel(const uint8_t* __restrict__ points, const uint8_t* __restrict__ scalars, uint32_t m,
                                                             const uint8_t* __restrict__ aux, const uint8_t* __restrict__ corr,
-                                                            uint8_t* __restrict__ results, uint8_t* __restrict__ witness, uint32_t* __restrict__ status) {
+                                                            uint8_t* __restrict__ results, uint8_t* __restrict__ witness, uint32_t* __restrict__ status,
+                                                            uint8_t* __restrict__ scratch) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     uint8_t* w = witness + 32ull * MV_LEN * i;
+    uint8_t* pts = scratch + MV_SCRATCH * i;
+    uint8_t* prefix = pts + 128ull * MV_PTS;
     const Affine pa = Affine::load(points + 64ull * i);
-    MvPoint P{pa.x, pa.y}, acc{Fq::load(aux), Fq::load(aux + 32)}, C{Fq::load(corr), Fq::load(corr + 32)};
+    const MvPoint P{pa.x, pa.y}, A0{Fq::load(aux), Fq::load(aux + 32)}, C{Fq::load(corr), Fq::load(corr + 32)};
     uint32_t st = 0;
     if (pa.is_identity()) st = 0xffffffffu;
     const Fr s = Fr::load(scalars + 32ull * i).from_mont();
-    for (uint32_t b = 0; b < MV_BITS; b++) {
-        uint32_t bit[1] = {(s.l[b >> 5] >> (b & 31)) & 1u};
-        store_small(w + 32ull * b, bit, 1);
-    }
-    for (uint32_t step = 0; step < MV_BITS && !st; step++) {
-        uint8_t* base = w + 32ull * (MV_BITS + (size_t)step * MV_STEP);
-        const uint32_t b = MV_BITS - 1 - step;
-        MvPoint D, T;
-        mv_double(base, acc, D);
-        if (!mv_add(base + 32 * 4 * MV_REC, D, P, T)) { st = 1 + step; break; }
-        store_point(base + 32 * 7 * MV_REC, D);
-        acc = ((s.l[b >> 5] >> (b & 31)) & 1u) ? T : D;
-        store_point(base + 32 * (7 * MV_REC + 8), acc);
+    auto bit_of = [&](uint32_t b) { return (s.l[b >> 5] >> (b & 31)) & 1u; };
+    for (uint32_t b = 0; b < MV_BITS; b++) (bit_of(b) ? Fr::one() : Fr::zero()).store(w + 32ull * b);
+
+    // ---- the ladder in XYZZ coordinates; an addition that meets equal x coordinates ends it
+    if (!st) {
+        XYZZ acc = XYZZ::from_affine(Affine{A0.x, A0.y});
+        for (uint32_t step = 0; step < MV_BITS; step++) {
+            const XYZZ D = acc.dbl();
+            if ((P.x * D.zz - D.x).is_zero()) { st = 1 + step; break; }
+            XYZZ T = D;
+            T.add_affine(Affine{P.x, P.y}, false);
+            D.store(pts + 128ull * (2 * step));
+            T.store(pts + 128ull * (2 * step + 1));
+            acc = bit_of(MV_BITS - 1 - step) ? T : D;
+        }
+        if (!st) {
+            if ((C.x * acc.zz - acc.x).is_zero()) st = 1 + MV_BITS;
+            else {
+                acc.add_affine(Affine{C.x, C.y}, false);
+                if (acc.is_identity()) st = 1 + MV_BITS;
+                else acc.store(pts + 128ull * (MV_PTS - 1));
+            }
+        }
     }
     MvPoint Q{Fq::zero(), Fq::zero()};
     if (!st) {
-        uint8_t* base = w + 32ull * (MV_BITS + (size_t)MV_BITS * MV_STEP);
-        if (!mv_add(base, acc, C, Q)) st = 1 + MV_BITS;
-        else store_point(base + 32 * 3 * MV_REC, Q);
+        // ---- first shared inversion: 1 / zzz of every point -> affine x, y in the first 64 bytes of its slot
+        mv_batch_invert(pts + 96, 128, MV_PTS, prefix);
+        for (uint32_t k = 0; k < MV_PTS; k++) {
+            uint8_t* q = pts + 128ull * k;
+            const Fq zi = Fq::load(q + 96), zzi = (zi * Fq::load(q + 64)).sqr();
+            (Fq::load(q) * zzi).store(q);
+            (Fq::load(q + 32) * zi).store(q + 32);
+        }
+        // ---- denominators: slot 2s: 2 y of the point step s doubles; slot 2s+1: xP - xD_s; last slot: xC - x of the final acc
+        MvPoint acc = A0;
+        for (uint32_t step = 0; step < MV_BITS; step++) {
+            uint8_t* qd = pts + 128ull * (2 * step);
+            acc.y.dbl().store(qd + 64);
+            (P.x - Fq::load(qd)).store(qd + 128 + 64);
+            const uint8_t* sel = bit_of(MV_BITS - 1 - step) ? qd + 128 : qd;
+            acc.x = Fq::load(sel); acc.y = Fq::load(sel + 32);
+        }
+        (C.x - acc.x).store(pts + 128ull * (MV_PTS - 1) + 64);
+        // ---- second shared inversion; the records are written by mulvar_records_kernel, one thread per step
+        mv_batch_invert(pts + 64, 128, MV_PTS, prefix);
+        const uint8_t* ql = pts + 128ull * (MV_PTS - 1);
+        Q.x = Fq::load(ql); Q.y = Fq::load(ql + 32);
     }
-    if (st) { Q.x = Fq::zero(); Q.y = Fq::zero(); }
     Q.x.store(results + 64ull * i);
     Q.y.store(results + 64ull * i + 32);
     status[i] = st;
+}
+
+// Second kernel: one thread per (mul_var, step).  After the ladder kernel every step's inputs are in the scratch — the affine point it
+// doubles (AUX for step 0, else the D or T slot of step s-1 by the scalar's bit) and its two inverted denominators — so the 255 steps
+// of a multiplication (254 ladder steps + the final correction) are independent and the records, 98 % of the work, fill the machine.
+__global__ void __launch_bounds__(128) mulvar_records_kernel(const uint8_t* __restrict__ points, const uint8_t* __restrict__ scalars, uint32_t m,
+                                                            const uint8_t* __restrict__ aux, const uint8_t* __restrict__ corr,
+                                                            uint8_t* __restrict__ witness, const uint32_t* __restrict__ status,
+                                                            const uint8_t* __restrict__ scratch) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = t / (MV_BITS + 1), step = t % (MV_BITS + 1);
+    if (i >= m || status[i]) return;
+    uint8_t* w = witness + 32ull * MV_LEN * i;
+    const uint8_t* pts = scratch + MV_SCRATCH * i;
+    const Fr s = Fr::load(scalars + 32ull * i).from_mont();
+    auto bit_of = [&](uint32_t b) { return (s.l[b >> 5] >> (b & 31)) & 1u; };
+    MvPoint acc;
+    if (step == 0) { acc.x = Fq::load(aux); acc.y = Fq::load(aux + 32); }
+    else {
+        const uint8_t* prev = pts + 128ull * (2 * (step - 1) + bit_of(MV_BITS - step));   // step s-1 consumed bit 253 - (s-1)
+        acc.x = Fq::load(prev); acc.y = Fq::load(prev + 32);
+    }
+    if (step < MV_BITS) {
+        const Affine pa = Affine::load(points + 64ull * i);
+        const MvPoint P{pa.x, pa.y};
+        uint8_t* base = w + 32ull * (MV_BITS + (size_t)step * MV_STEP);
+        const uint8_t* qd = pts + 128ull * (2 * step);
+        MvPoint D, T;
+        mv_double(base, acc, Fq::load(qd + 64), D);
+        mv_add(base + 32 * 4 * MV_REC, D, P, Fq::load(qd + 128 + 64), T);
+        store_point(base + 32 * 7 * MV_REC, D);
+        store_point(base + 32 * (7 * MV_REC + 8), bit_of(MV_BITS - 1 - step) ? T : D);
+    } else {
+        const MvPoint C{Fq::load(corr), Fq::load(corr + 32)};
+        uint8_t* base = w + 32ull * (MV_BITS + (size_t)MV_BITS * MV_STEP);
+        MvPoint Q;
+        mv_add(base, acc, C, Fq::load(pts + 128ull * (MV_PTS - 1) + 64), Q);
+        store_point(base + 32 * 3 * MV_REC, Q);
+    }
 }
 
 }  // namespace
@@ -263,9 +388,21 @@ int h2a_mulvar_witness_dev(h2a_ctx* ctx, const void* d_points, const void* d_sca
     uint8_t* d_small = (uint8_t*)ctx->misc.p;
     uint32_t* d_status = (uint32_t*)(d_small + 128);
     H2A_CUDA(ctx, cudaMemcpyAsync(d_small, small, 128, cudaMemcpyHostToDevice, ctx->stream));
-    mulvar_witness_kernel<<<(unsigned)((m + 31) / 32), 32, 0, ctx->stream>>>((const uint8_t*)d_points, (const uint8_t*)d_scalars, (uint32_t)m, d_small,
-                                                                              d_small + 64, (uint8_t*)d_results, (uint8_t*)d_witness, d_status);
-    H2A_LAUNCH_CHECK(ctx);
+    // ladder scratch (81 KB per entry): at most MV_CHUNK entries per launch
+    constexpr size_t MV_CHUNK = 8192;
+    H2A_TRY(h2a_reserve(ctx, ctx->aff_a, MV_SCRATCH * std::min(m, MV_CHUNK)));
+    for (size_t lo = 0; lo < m; lo += MV_CHUNK) {
+        const size_t cnt = std::min(MV_CHUNK, m - lo);
+        mulvar_witness_kernel<<<(unsigned)((cnt + 31) / 32), 32, 0, ctx->stream>>>(
+            (const uint8_t*)d_points + 64 * lo, (const uint8_t*)d_scalars + 32 * lo, (uint32_t)cnt, d_small, d_small + 64, (uint8_t*)d_results + 64 * lo,
+            (uint8_t*)d_witness + 32ull * MV_LEN * lo, d_status + lo, (uint8_t*)ctx->aff_a.p);
+        H2A_LAUNCH_CHECK(ctx);
+        const size_t threads = cnt * (MV_BITS + 1);
+        mulvar_records_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(
+            (const uint8_t*)d_points + 64 * lo, (const uint8_t*)d_scalars + 32 * lo, (uint32_t)cnt, d_small, d_small + 64,
+            (uint8_t*)d_witness + 32ull * MV_LEN * lo, d_status + lo, (const uint8_t*)ctx->aff_a.p);
+        H2A_LAUNCH_CHECK(ctx);
+    }
     std::vector<uint32_t> st(m);
     H2A_CUDA(ctx, cudaMemcpyAsync(st.data(), d_status, 4 * m, cudaMemcpyDeviceToHost, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

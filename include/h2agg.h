@@ -296,8 +296,8 @@ const char* h2a_prove_phase_name(const h2a_ctx* ctx, int index);
  * scalars: src/multiopen.rs:393 (z_i W_i), :443 (Horner chain of commitments), :474,480,486 (W, ZW, F), :492 (E),
  * src/vanishing.rs:181-187 (quotient pieces) — about 37 per aggregated proof.  The chip (halo2wrong, not in the tree) holds an Fq
  * coordinate as 4 limbs of 68 bits in Fr cells (examples/simple-example.rs:396-397, packing as :535-548) and witnesses every Fq
- * product a*b = q*p + r with limb products.  h2a_mulvar_witness fills those cells for m independent (point, scalar) pairs in one
- * launch, one thread per pair: out_results[i] = scalars[i] * points[i] (affine) and h2a_mulvar_witness_len() Fr elements per
+ * product a*b = q*p + r with limb products.  h2a_mulvar_witness fills those cells for m independent (point, scalar) pairs at once
+ * (one thread per pair walks the ladder, one thread per pair and step writes the records): out_results[i] = scalars[i] * points[i] (affine) and h2a_mulvar_witness_len() Fr elements per
  * pair in the layout documented in csrc/mulvar.cu (bits of the scalar, then per bit the records of one doubling and one
  * addition, limbs of the intermediate points, a final correction by -(2^254 aux)).  `aux` is the auxiliary point the incomplete
  * affine additions start from.  An entry whose ladder meets equal x coordinates (scalar 0, the identity as input, ...) cannot be
