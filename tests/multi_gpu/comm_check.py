@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Checks the library's own multi-GPU plumbing (csrc/comm.cu) under torchrun, one process per GPU:
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/comm_check.py
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/multi_gpu/comm_check.py
 allgather of raw bytes (host and device buffers), broadcast, and one MSM over per-rank point ranges compared with the
 oracle's best_multiexp over all the points.  torch.distributed only carries the two unique ids and the final verdict."""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

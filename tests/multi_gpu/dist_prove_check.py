@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Parity of ONE proof spread over several GPUs (native distribution, csrc/comm.cu + plonk_prove.cu) under torchrun:
-  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/dist_prove_check.py
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tests/multi_gpu/dist_prove_check.py
 every rank proves the test circuits of tests/circuits.py with the library and the bytes must equal the ORACLE prover's
 (oracle/plonk.py) on every rank; a lookup input outside its table must fail on every rank (no rank left in a collective)."""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

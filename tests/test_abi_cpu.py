@@ -222,7 +222,7 @@ def test_header_is_valid_c_and_smoke_program_compiles(tmp_path):
     on the GPU box, tests/test_gpu_abi_c.py); its known answers are current with the oracle's big-integer model."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = _run_tool("tools/gen_abi_smoke_kat.py", "--check")
+    r = _run_tool("tests/c/gen_abi_smoke_kat.py", "--check")
     assert r.returncode == 0, r.stdout + r.stderr
     exe = str(tmp_path / "abi_smoke")
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_smoke.c"),

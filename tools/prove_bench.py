@@ -230,11 +230,10 @@ def main():
     else:
         import hashlib
         res["proof_sha256"] = hashlib.sha256(res.pop("proof_digest_src")).hexdigest()
-    if args.rank == 0 and args.oracle_check:   # the oracle's verifier (oracle/plonk.py) replays the proof: O(proof size), any k
-        import bench_extras
-        from oracle import loader as orc, plonk as pk, pymodel as pm
-        orc.load()
-        ok, _ = bench_extras._oracle_accepts(dict(pk=pk, pm=pm), res["_check"])
+    if args.rank == 0 and args.oracle_check:   # the oracle's verifier replays the proof (tests/oracle_checks.py: test infrastructure)
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_checks
+        ok = oracle_checks.proof_accepted(res["_check"])
         res["parity_checked"] = "oracle verifier (oracle/plonk.py verify_proof + pairing relation)" if ok else "ORACLE VERIFIER REJECTS THE PROOF"
         res["proof_verifies"] = res["proof_verifies"] and ok
     if args.rank == 0:
