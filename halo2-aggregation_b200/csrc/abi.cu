@@ -141,8 +141,9 @@ static int msm_host_split(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, c
     alt->msm_algo = ctx->msm_algo;
     h2a_ctx* lanes[2] = {ctx, alt};
     const int pieces = ctx->msm_host_split;
-    // the first range is the only one whose copy is exposed: it gets a smaller share, the rest is cut evenly
-    int first_pct = 100 / pieces;
+    // the first range is the only one whose copy is exposed: it gets a smaller share, the rest is cut evenly (two ranges, 2^22
+    // points, measured per call: 35 % 10.95 ms, 42 % 10.90, 50 % 11.06, 58 % 11.45)
+    int first_pct = pieces == 2 ? 42 : 100 / pieces;
     if (const char* env = getenv("H2A_MSM_HOST_FIRST_PCT")) first_pct = std::max(1, std::min(99, atoi(env)));
     const size_t first_len = std::min(n, (n * (size_t)first_pct / 100 + 1023) & ~(size_t)1023);
     const size_t piece_len = pieces > 1 ? (n - first_len + pieces - 2) / (pieces - 1) : 0;
