@@ -7,6 +7,7 @@
 
 #include "ctx.hpp"
 #include "host_bn254.hpp"
+#include "dist_layout.hpp"
 #include "tree_layout.hpp"
 
 int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
@@ -119,6 +120,14 @@ int h2a_tree_layout(uint64_t total_padded, int rounds, int half, int round, int6
     out6[0] = in.array; out6[1] = (int64_t)in.first; out6[2] = (int64_t)in.count;
     out6[3] = out.array; out6[4] = (int64_t)out.first; out6[5] = (int64_t)out.count;
     return H2A_OK;
+}
+
+int h2a_dist_window(uint32_t m, int world, int rank, uint32_t halo, uint32_t out4[4]) {
+    if (!out4 || world < 2 || rank < 0 || rank >= world || m == 0 || m % (uint32_t)world || 2ull * halo > m / (uint32_t)world) return H2A_ERR_INVALID;
+    DistPiece piece[2] = {{0, 0}, {0, 0}};
+    const int n = dist_window(m, world, rank, halo, piece);
+    out4[0] = piece[0].first; out4[1] = piece[0].count; out4[2] = piece[1].first; out4[3] = piece[1].count;
+    return n;
 }
 
 int h2a_msm_g1_dev(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, const void* d_scalars, size_t n,

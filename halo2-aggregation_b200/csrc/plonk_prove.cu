@@ -17,6 +17,7 @@
 
 #include "field.cuh"
 #include "host_glue.hpp"
+#include "dist_layout.hpp"
 #include "plonk.hpp"
 
 int h2a_ntt_run(h2a_ctx* ctx, const uint8_t* d_src, uint32_t n_in, uint8_t* d_work, uint8_t* d_dst, uint32_t log_n,
@@ -740,13 +741,10 @@ int transform_columns(h2a_ctx* ctx, h2a_circuit* c, const std::vector<Poly3*>& c
                 if (!slice || halo == UINT32_MAX) { H2A_TRY(h2a_comm_broadcast_on(ctx, 1, cols[j]->ext, 32ull * m, owner[j], lane)); continue; }
                 for (int r = 0; r < W; r++) {
                     if (r == owner[j] || (me != owner[j] && me != r)) continue;
-                    // window of rank r: [r slice - halo, (r + 1) slice + halo) mod m, as one or two contiguous pieces
-                    uint32_t lo[2], len[2];
-                    int pieces = 0;
-                    const int64_t a = (int64_t)r * slice - halo, b = (int64_t)(r + 1) * slice + halo;
-                    if (a < 0) { lo[pieces] = (uint32_t)(a + m); len[pieces++] = (uint32_t)(-a); lo[pieces] = 0; len[pieces++] = (uint32_t)b; }
-                    else if (b > (int64_t)m) { lo[pieces] = (uint32_t)a; len[pieces++] = (uint32_t)(m - a); lo[pieces] = 0; len[pieces++] = (uint32_t)(b - m); }
-                    else { lo[pieces] = (uint32_t)a; len[pieces++] = (uint32_t)(b - a); }
+                    // window of rank r: [r slice - halo, (r + 1) slice + halo) mod m, as one or two contiguous pieces (dist_layout.hpp)
+                    DistPiece piece[2];
+                    const int pieces = dist_window(m, W, r, halo, piece);
+                    uint32_t lo[2] = {piece[0].first, piece[1].first}, len[2] = {piece[0].count, piece[1].count};
                     for (int q = 0; q < pieces; q++) {
                         if (me == owner[j]) H2A_TRY(h2a_comm_send_on(ctx, 1, cols[j]->ext + 32ull * lo[q], 32ull * len[q], r, lane));
                         else H2A_TRY(h2a_comm_recv_on(ctx, 1, cols[j]->ext + 32ull * lo[q], 32ull * len[q], owner[j], lane));

@@ -335,6 +335,11 @@ int h2a_field_op(h2a_ctx* ctx, int field, int op, const uint8_t* a, const uint8_
  * out array, out first, out count}; arrays 0/1/2 are the three point arrays, -1 the sorted entries.  The halves run on two
  * unordered streams, so their spans must never meet before the join: tests/test_abi_cpu.py checks that. */
 int h2a_tree_layout(uint64_t total_padded, int rounds, int half, int round, int64_t out6[6]);
+/* Test hook, no device needed: the rows of an extended-domain column (m rows) that rank `rank` of `world` holds when one proof is
+ * spread over several GPUs — its m / world rows of the quotient plus `halo` rows on either side, modulo m — as one or two
+ * contiguous pieces out4 = {first, count, first, count} (csrc/dist_layout.hpp).  Returns the number of pieces, or H2A_ERR_INVALID
+ * (world < 2, m not a multiple of world, 2 * halo > m / world: whole columns are broadcast then). */
+int h2a_dist_window(uint32_t m, int world, int rank, uint32_t halo, uint32_t out4[4]);
 /* Element-wise device point arithmetic: op 0: out[i] = a[i] + b[i]; op 1: out[i] = 2*a[i]. Affine in/out. */
 int h2a_g1_op(h2a_ctx* ctx, int op, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n);
 /* Per-phase device times of the most recent MSM / NTT on this ctx, measured with CUDA events on the

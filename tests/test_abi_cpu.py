@@ -245,3 +245,42 @@ def test_generated_field_square_is_current_and_checked():
         parts.append(g.emit(g.build("sqr", p_int), "mont_sqr_wide", "sqr", field))
     parts.append("}  // namespace h2a\n")
     assert open(g.OUT).read() == "\n\n".join(parts)
+
+
+def test_distributed_prover_windows_cover_what_a_rank_reads():
+    """One proof over several GPUs: rank r evaluates quotient rows [r m/W, (r+1) m/W) and reads its columns at row + rot * step, so
+    the window of an extended column it is sent (h2a_dist_window, csrc/dist_layout.hpp) must hold every such row; the pieces are
+    contiguous, inside the array, disjoint, and together exactly slice + 2 halo rows."""
+    import ctypes
+    lib = h2a.load_library()
+    out = (ctypes.c_uint32 * 4)()
+    for m in (1 << 12, 1 << 16, 3 << 10, 1 << 22):
+        for world in (2, 3, 4, 8):
+            if m % world:
+                continue
+            slice_ = m // world
+            for halo in (0, 4, 24, slice_ // 4, slice_ // 2):
+                held = []
+                for rank in range(world):
+                    n = lib.h2a_dist_window(ctypes.c_uint32(m), world, rank, ctypes.c_uint32(halo), out)
+                    assert n in (1, 2)
+                    pieces = [(out[0], out[1]), (out[2], out[3])][:n]
+                    rows = set()
+                    for first, count in pieces:
+                        assert count > 0 and first + count <= m
+                        new = set(range(first, first + count)) if m <= (1 << 16) else None
+                        if new is not None:
+                            assert not (rows & new)
+                            rows |= new
+                    assert sum(c for _, c in pieces) == slice_ + 2 * halo
+                    if m <= (1 << 16):
+                        lo, hi = rank * slice_, (rank + 1) * slice_
+                        for i in (lo, lo + 1, (lo + hi) // 2, hi - 1):
+                            for d in (-halo, -min(1, halo), 0, min(1, halo), halo):
+                                assert (i + d) % m in rows, (m, world, rank, halo, i, d)
+                        assert rows == {x % m for x in range(lo - halo, hi + halo)}
+                    held.append(pieces)
+    bad = (ctypes.c_uint32 * 4)()
+    assert lib.h2a_dist_window(ctypes.c_uint32(1 << 12), 1, 0, ctypes.c_uint32(4), bad) == -1        # one rank needs no window
+    assert lib.h2a_dist_window(ctypes.c_uint32(1 << 12), 3, 0, ctypes.c_uint32(4), bad) == -1        # m not a multiple of world
+    assert lib.h2a_dist_window(ctypes.c_uint32(1 << 12), 4, 0, ctypes.c_uint32(600), bad) == -1      # reach wider than half a slice
