@@ -212,6 +212,24 @@ def gwc_accumulate(commitments, rotations, evals, ws, x, u, v, omega, g1):
     return out
 
 
+def mulvar_witness_len():
+    fn = load().orc_mulvar_witness_len
+    fn.restype = ctypes.c_size_t
+    return int(fn())
+
+
+def mulvar_witness(points, scalars, aux, want_cells=True, threads=None):
+    """C++ restatement of oracle/mulvar.py: (results m*64, cells m*len*32 or None, status u32[m])"""
+    points, scalars, aux = _c(points), _c(scalars), _c(aux)
+    m = scalars.size // 32
+    assert points.size == 64 * m and aux.size == 64
+    res, status = _u8(64 * m), np.zeros(m, np.uint32)
+    cells = _u8(32 * mulvar_witness_len() * m) if want_cells else None
+    load().orc_mulvar_witness(_p(points), _p(scalars), ctypes.c_size_t(m), _p(aux), _p(res), _p(cells) if want_cells else None,
+                              status.ctypes.data_as(ctypes.c_void_p), threads or hw_threads())
+    return res, cells, status
+
+
 def fold_h(h_pieces, xn):
     h = _c(h_pieces)
     out = _u8(64)

@@ -301,6 +301,131 @@ struct Transcript {  // Blake2bWrite / Blake2bRead state with Challenge255
 }  // namespace
 
 // ====================================================================== C ABI (ctypes)
+// ---- non-native mul_var witness cells (row f4): the same cells as oracle/mulvar.py, compiled, so that the benchmark has a CPU
+// figure that is not an interpreter's.  Written the way sequential witness code computes them — one field inversion per affine
+// formula, 512-bit product and exact quotient per record — cell order as documented in csrc/mulvar.cu; checked cell for cell against
+// the Python big-integer statement in tests/test_mulvar_oracle.py.  halo2wrong (Cargo.toml:10) is not in the tree: PARITY UNPINNED.
+namespace mulvar {
+constexpr int BITS = 254, REC = 22, STEP = 7 * REC + 16, FINAL = 3 * REC + 8, LEN = BITS + BITS * STEP + FINAL;
+typedef unsigned __int128 u128;
+struct W4 { uint64_t w[4]; };   // up to 256 bits
+inline W4 w4(uint64_t lo = 0) { W4 r{{lo, 0, 0, 0}}; return r; }
+inline void add(W4& a, const W4& b) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)a.w[i] + b.w[i]; a.w[i] = (uint64_t)c; c >>= 64; } }
+inline void sub(W4& a, const W4& b) { u128 br = 0; for (int i = 0; i < 4; i++) { u128 d = (u128)a.w[i] - b.w[i] - br; a.w[i] = (uint64_t)d; br = (d >> 64) & 1; } }
+inline W4 shl68(const W4& a) { W4 r = w4(); for (int i = 0; i < 3; i++) { r.w[i + 1] |= a.w[i] << 4; if (i + 2 < 4) r.w[i + 2] |= a.w[i] >> 60; } return r; }
+inline W4 shr136(const W4& a) { W4 r = w4(); r.w[0] = (a.w[2] >> 8) | (a.w[3] << 56); r.w[1] = a.w[3] >> 8; return r; }
+struct Limb { uint64_t lo, hi; };   // 68 bits: hi < 16
+inline Limb limb_of(const uint64_t v[4], int i) {
+    const int bit = 68 * i, w = bit >> 6, sh = bit & 63;
+    const uint64_t x0 = v[w], x1 = w + 1 < 4 ? v[w + 1] : 0, x2 = w + 2 < 4 ? v[w + 2] : 0;
+    Limb l;
+    l.lo = sh ? (x0 >> sh) | (x1 << (64 - sh)) : x0;
+    l.hi = (sh ? (x1 >> sh) | (x2 << (64 - sh)) : x1) & 0xf;
+    return l;
+}
+inline W4 mul68(const Limb& a, const Limb& b) {   // 136 bits
+    W4 r = w4();
+    u128 p = (u128)a.lo * b.lo;
+    r.w[0] = (uint64_t)p; r.w[1] = (uint64_t)(p >> 64);
+    u128 mid = (u128)a.lo * b.hi + (u128)b.lo * a.hi;            // < 2^69
+    W4 m = w4(); m.w[1] = (uint64_t)mid; m.w[2] = (uint64_t)(mid >> 64);
+    add(r, m);
+    W4 h = w4(); h.w[2] = a.hi * b.hi;
+    add(r, h);
+    return r;
+}
+inline Fr cell(const W4& v) { return Fr::from_raw(v.w); }          // values are far below r
+inline Fr cell(const Limb& l) { uint64_t t[4] = {l.lo, l.hi, 0, 0}; return Fr::from_raw(t); }
+// p' = 2^272 - p as four 68-bit limbs; p^-1 mod 2^256
+static const Limb NEG_P[4] = {{0xc3df73e9278302b9ull, 0x2}, {0x2687e956e978e357ull, 0xa}, {0xd647afba497e7ea7ull, 0xf}, {0xfffcf9bb18d1ece5ull, 0xf}};
+static const uint64_t P_INV[4] = {0x782df87d1b799c77ull, 0x6121829ae1359536ull, 0x2750342fe7cc257full, 0x0a85dd486e777394ull};
+inline void mul_low(const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+    uint64_t r[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) { u128 c = 0; for (int j = 0; i + j < 4; j++) { c += (u128)a[i] * b[j] + r[i + j]; r[i + j] = (uint64_t)c; c >>= 64; } }
+    for (int i = 0; i < 4; i++) out[i] = r[i];
+}
+// cells of a * b = q p + r; returns r (Montgomery)
+inline Fq record(const Fq& a_m, const Fq& b_m, Fr* out) {
+    const Fq r_m = a_m * b_m;
+    uint64_t a[4], b[4], r[4], lo[4], q[4];
+    a_m.to_raw(a); b_m.to_raw(b); r_m.to_raw(r);
+    mul_low(a, b, lo);
+    { u128 br = 0; for (int i = 0; i < 4; i++) { u128 d = (u128)lo[i] - r[i] - br; lo[i] = (uint64_t)d; br = (d >> 64) & 1; } }
+    mul_low(lo, P_INV, q);
+    Limb al[4], bl[4], ql[4], rl[4];
+    for (int i = 0; i < 4; i++) { al[i] = limb_of(a, i); bl[i] = limb_of(b, i); ql[i] = limb_of(q, i); rl[i] = limb_of(r, i); }
+    for (int i = 0; i < 4; i++) { out[i] = cell(al[i]); out[4 + i] = cell(bl[i]); out[8 + i] = cell(ql[i]); out[12 + i] = cell(rl[i]); }
+    W4 t[4];
+    for (int k = 0; k < 4; k++) {
+        t[k] = w4();
+        for (int i = 0; i <= k; i++) { add(t[k], mul68(al[i], bl[k - i])); add(t[k], mul68(ql[i], NEG_P[k - i])); }
+        out[16 + k] = cell(t[k]);
+    }
+    W4 v = w4();
+    for (int half = 0; half < 2; half++) {
+        W4 u = t[2 * half];
+        add(u, shl68(t[2 * half + 1]));
+        add(u, v);
+        W4 rr = w4(), r1 = w4();
+        rr.w[0] = rl[2 * half].lo; rr.w[1] = rl[2 * half].hi;
+        r1.w[0] = rl[2 * half + 1].lo; r1.w[1] = rl[2 * half + 1].hi;
+        add(rr, shl68(r1));
+        sub(u, rr);
+        v = shr136(u);
+        out[20 + half] = cell(v);
+    }
+    return r_m;
+}
+inline void point_cells(const G1Affine& p, Fr* out) {
+    uint64_t x[4], y[4];
+    p.x.to_raw(x); p.y.to_raw(y);
+    for (int i = 0; i < 4; i++) { out[i] = cell(limb_of(x, i)); out[4 + i] = cell(limb_of(y, i)); }
+}
+inline bool add_cells(const G1Affine& a, const G1Affine& b, Fr* out, G1Affine& res) {
+    const Fq dx = b.x - a.x;
+    if (dx.is_zero()) return false;
+    const Fq lam = (b.y - a.y) * dx.inv();
+    record(lam, dx, out);
+    const Fq l2 = record(lam, lam, out + REC);
+    res.x = l2 - a.x - b.x;
+    res.y = record(lam, a.x - res.x, out + 2 * REC) - a.y;
+    return true;
+}
+inline void double_cells(const G1Affine& a, Fr* out, G1Affine& res) {
+    const Fq xx = record(a.x, a.x, out);
+    const Fq y2 = a.y.dbl();
+    const Fq lam = (xx.dbl() + xx) * y2.inv();
+    record(lam, y2, out + REC);
+    const Fq l2 = record(lam, lam, out + 2 * REC);
+    res.x = l2 - a.x.dbl();
+    res.y = record(lam, a.x - res.x, out + 3 * REC) - a.y;
+}
+// one mul_var; returns the status (0 ok, 1 + step, 0xffffffff identity input)
+inline uint32_t witness(const G1Affine& P, const Fr& s, const G1Affine& aux, const G1Affine& corr, Fr* cells, G1Affine& Q) {
+    uint64_t e[4];
+    s.to_raw(e);
+    auto bit = [&](int b) { return (e[b >> 6] >> (b & 63)) & 1; };
+    for (int b = 0; b < BITS; b++) cells[b] = bit(b) ? Fr::one() : Fr::zero();
+    Q = G1Affine::identity();
+    if (P.is_identity()) return 0xffffffffu;
+    G1Affine acc = aux;
+    for (int step = 0; step < BITS; step++) {
+        Fr* base = cells + BITS + (size_t)step * STEP;
+        G1Affine D, T;
+        double_cells(acc, base, D);
+        if (!add_cells(D, P, base + 4 * REC, T)) return 1 + step;
+        point_cells(D, base + 7 * REC);
+        acc = bit(BITS - 1 - step) ? T : D;
+        point_cells(acc, base + 7 * REC + 8);
+    }
+    Fr* base = cells + BITS + (size_t)BITS * STEP;
+    if (!add_cells(acc, corr, base, Q)) { Q = G1Affine::identity(); return 1 + BITS; }
+    point_cells(Q, base + 3 * REC);
+    return 0;
+}
+}  // namespace mulvar
+
+
 extern "C" {
 
 int orc_hw_threads() { return (int)std::thread::hardware_concurrency(); }
@@ -497,6 +622,25 @@ int orc_gwc_accumulate(const uint8_t* commitments, const int32_t* rotations, con
 }
 
 // H = sum_i (x^n)^i h_i  as the reference folds it (src/vanishing.rs:177-188):
+size_t orc_mulvar_witness_len() { return mulvar::LEN; }
+// m independent mul_var over the host threads; cells may be NULL (results and status only)
+void orc_mulvar_witness(const uint8_t* points, const uint8_t* scalars, size_t m, const uint8_t aux_[64], uint8_t* results, uint8_t* cells,
+                        uint32_t* status, int threads) {
+    const G1Affine aux = load_affine(aux_);
+    G1 c = G1::from_affine(aux);
+    for (int i = 0; i < mulvar::BITS; i++) c = c.dbl();
+    const G1Affine corr = c.to_affine().neg();
+    parallel_for(m, threads, [&](size_t lo, size_t hi, int) {
+        std::vector<Fr> tmp(cells ? 0 : mulvar::LEN);
+        for (size_t i = lo; i < hi; i++) {
+            Fr* out = cells ? (Fr*)(cells + 32ull * mulvar::LEN * i) : tmp.data();
+            G1Affine q;
+            status[i] = mulvar::witness(load_affine(points + 64 * i), load_fr(scalars + 32 * i), aux, corr, out, q);
+            store_affine(results + 64 * i, q);
+        }
+    });
+}
+
 // H starts at h_0; each later piece is multiplied by a running power of x^n and added.
 void orc_fold_h(const uint8_t* h_pieces, size_t n_pieces, const uint8_t xn_[32], uint8_t out[64]) {
     Fr xn = load_fr(xn_), xn_power = xn;

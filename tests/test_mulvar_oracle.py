@@ -3,6 +3,8 @@
 (examples/simple-example.rs:535-537; SURVEY App. A known answer), and its result is s*P of the curve model."""
 import random
 
+import numpy as np
+
 from oracle import mulvar as mv
 from oracle import pymodel as pm
 
@@ -47,3 +49,27 @@ def test_witness_of_one_mul_var():
     assert mv.mulvar_witness(pm.g1_mul(pm.G1, 5), 0, aux)[2] == 1 + mv.BITS          # s = 0: the final addition cancels
     assert mv.mulvar_witness(None, 7, aux)[2] == 0xffffffff                            # the identity has no affine cells
     assert mv.mulvar_witness(pm.g1_mul(aux, 2), 7, aux)[2] == 1                        # first addition meets P = 2 aux
+
+
+def test_compiled_restatement_matches_the_big_integer_one(orc):
+    """oracle/oracle.cpp `orc_mulvar_witness` (the compiled CPU figure of the benchmark, and the checker of large batches) writes the
+    cells of oracle/mulvar.py, cell for cell, and reports the same status for what cannot be witnessed."""
+    rng = random.Random(3)
+    aux = pm.g1_mul(pm.G1, 0xabcdef123457)
+    pts = [pm.g1_mul(pm.G1, rng.randrange(1, pm.R)) for _ in range(4)] + [None, pm.g1_mul(aux, 2)]
+    sc = [1, pm.R - 1, rng.randrange(pm.R), 0, 7, 7]
+    pb = np.frombuffer(b"".join(pm.affine_bytes(p) for p in pts), dtype=np.uint8)
+    sb = np.frombuffer(b"".join(pm.fr_mont_bytes(s) for s in sc), dtype=np.uint8)
+    ab = np.frombuffer(pm.affine_bytes(aux), dtype=np.uint8)
+    assert orc.mulvar_witness_len() == mv.LEN
+    res, cells, status = orc.mulvar_witness(pb, sb, ab)
+    for i, (p, s) in enumerate(zip(pts, sc)):
+        q, want, st = mv.mulvar_witness(p, s, aux)
+        assert st == status[i]
+        if st == 0:
+            assert bytes(cells[32 * mv.LEN * i:32 * mv.LEN * (i + 1)]) == b"".join(pm.fr_mont_bytes(c) for c in want)
+            assert pm.affine_from_bytes(bytes(res[64 * i:64 * i + 64])) == q
+        else:
+            assert bytes(res[64 * i:64 * i + 64]) == bytes(64)
+    res2, none, status2 = orc.mulvar_witness(pb, sb, ab, want_cells=False, threads=2)
+    assert none is None and bytes(res2) == bytes(res) and list(status2) == list(status)
