@@ -156,25 +156,28 @@ pub struct EvaluationDomain<'c> {
     ctx: &'c Context,
     pub k: u32,
     pub ext_k: u32,
+    quotient_poly_degree: usize,
     omega: [u8; 32],
     zeta: [u8; 32],
 }
 impl<'c> EvaluationDomain<'c> {
     /// `j` = the circuit's degree, as in `EvaluationDomain::new(j, k)`; `zeta` = the dependency's coset generator.
     pub fn new(ctx: &'c Context, j: u32, k: u32, zeta: [u8; 32]) -> Result<Self> {
+        assert!(j >= 2);
         let mut ext_k = k;
         while (1u64 << ext_k) < ((1u64 << k) * (j as u64 - 1)) {
             ext_k += 1;
         }
         let mut omega = [0u8; 32];
         ctx.check(unsafe { sys::h2a_fr_root_of_unity(k, omega.as_mut_ptr()) })?;
-        Ok(EvaluationDomain { ctx, k, ext_k, omega, zeta })
+        Ok(EvaluationDomain { ctx, k, ext_k, quotient_poly_degree: (j - 1) as usize, omega, zeta })
     }
     pub fn get_omega(&self) -> [u8; 32] {
         self.omega
     }
+    /// `j - 1`, as the dependency returns it (src/verifier.rs:431 reads it for the number of quotient pieces).
     pub fn get_quotient_poly_degree(&self) -> usize {
-        (1usize << (self.ext_k - self.k)).max(1)
+        self.quotient_poly_degree
     }
     pub fn lagrange_to_coeff<S>(&self, a: &mut [S]) -> Result<()> {
         assert_eq!(a.len(), 1usize << self.k);
@@ -321,6 +324,35 @@ pub fn fold_h(ctx: &Context, h_pieces: &[[u8; 64]], xn: &[u8; 32]) -> Result<[u8
     let mut out = [0u8; 64];
     ctx.check(unsafe { sys::h2a_fold_h(ctx.raw, h_pieces.as_ptr() as *const u8, h_pieces.len(), xn.as_ptr(), out.as_mut_ptr()) })?;
     Ok(out)
+}
+
+/// Witness cells of the non-native `ecc_chip.mul_var(region, point, scalar, offset)` of the aggregation circuit
+/// (src/multiopen.rs:393-492, src/vanishing.rs:181-187) for a batch of (point, scalar) pairs.
+pub struct MulVarWitness {
+    /// `scalars[i] * points[i]`, affine.
+    pub results: Vec<[u8; 64]>,
+    /// `mul_var_witness_len()` cells per pair (layout: csrc/mulvar.cu); empty when not asked for.
+    pub cells: Vec<[u8; 32]>,
+    /// 0 = witnessed; anything else: the incomplete additions met equal x coordinates (scalar 0, the identity, ...).
+    pub status: Vec<u32>,
+}
+pub fn mul_var_witness_len() -> usize {
+    unsafe { sys::h2a_mulvar_witness_len() }
+}
+/// `aux`: the auxiliary point the incomplete additions start from.  `Err` carries the library's message; when single
+/// entries cannot be witnessed the error code is `H2A_ERR_INVALID` and `status` of the returned error context names them.
+pub fn mul_var_witness(ctx: &Context, points: &[[u8; 64]], scalars: &[[u8; 32]], aux: &[u8; 64], want_cells: bool) -> std::result::Result<MulVarWitness, (Error, Vec<u32>)> {
+    assert_eq!(points.len(), scalars.len());
+    let m = points.len();
+    let mut w = MulVarWitness { results: vec![[0u8; 64]; m], cells: vec![[0u8; 32]; if want_cells { m * mul_var_witness_len() } else { 0 }], status: vec![0u32; m] };
+    let cells_ptr = if want_cells { w.cells.as_mut_ptr() as *mut u8 } else { ptr::null_mut() };
+    let rc = unsafe {
+        sys::h2a_mulvar_witness(ctx.raw, points.as_ptr() as *const u8, scalars.as_ptr() as *const u8, m, aux.as_ptr(), w.results.as_mut_ptr() as *mut u8, cells_ptr, w.status.as_mut_ptr())
+    };
+    match ctx.check(rc) {
+        Ok(()) => Ok(w),
+        Err(e) => Err((e, w.status)),
+    }
 }
 
 /// `Blake2bWrite<_, _, Challenge255<_>>` / `Blake2bRead` (src/transcript.rs:58,72,105-107,122-124).

@@ -231,6 +231,48 @@ def test_header_is_valid_c_and_smoke_program_compiles(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def _build_cpp_example(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "simple_example")
+    libdir = os.path.dirname(h2a.library_path())
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "examples", "simple_example.cpp"), "-L" + libdir, "-lh2agg", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_side_compiles_and_its_host_half_runs(tmp_path):
+    """include/h2agg.hpp — the host side above the C ABI in C++, the compiled twin of the Rust shim — and the C++ restatement of
+    the reference's example (examples/simple_example.cpp) build warning-free against the library; the half of the example that
+    needs no GPU (field helpers, 68-bit limb packing, circuit description, copy constraints -> permutation, transcript, the
+    XorShift secret) agrees with the oracle's known answers, which are current.  The GPU half: tests/test_gpu_abi_cpp.py."""
+    import subprocess
+    r = _run_tool("tests/c/gen_simple_example_kat.py", "--check")
+    assert r.returncode == 0, r.stdout + r.stderr
+    exe = _build_cpp_example(tmp_path)
+    r = subprocess.run([exe, "--host-only"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "host half: all ok" in r.stdout and "FAIL" not in r.stdout, r.stdout + r.stderr
+
+
+def test_cpp_host_side_covers_the_rust_shim_surface():
+    """The C++ header and the Rust shim are two statements of one interface: every h2a_* entry point the shim reaches is reached
+    by the header too, and both carry the dependency's names."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hpp = open(os.path.join(root, "include", "h2agg.hpp")).read()
+    shim = open(os.path.join(root, "h2agg-shim", "src", "lib.rs")).read()
+    used_hpp = set(re.findall(r"\b(h2a_[a-z0-9_]+)\(", hpp))
+    used_shim = set(re.findall(r"sys::(h2a_[a-z0-9_]+)\(", shim))
+    assert used_hpp <= set(h2a.declared_symbols()), used_hpp - set(h2a.declared_symbols())
+    assert used_shim <= used_hpp, used_shim - used_hpp
+    for name in ("best_multiexp", "best_fft", "EvaluationDomain", "lagrange_to_coeff", "coeff_to_extended", "extended_to_coeff", "get_omega",
+                 "get_quotient_poly_degree", "verifier_params", "commit_lagrange", "create_proof", "verify_proof", "verify_proof_batch",
+                 "verify_accumulate", "fold_h", "Transcript", "mul_var_witness", "comm_init", "allgather"):
+        assert name in hpp and name in shim, name
+
+
 def test_generated_field_square_is_current_and_checked():
     """csrc/field_mul_gen.cuh is what tools/gen_field_mul.py emits, and the generator's op lists still pass their check
     against Python big integers (random and edge operands, no carry dropped)."""
