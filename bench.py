@@ -340,23 +340,36 @@ def main():
                timed=timed, barrier=barrier, combine=combine, all_ranks_ok=all_ranks_ok, hbm_peak=hbm_peak, peak_src=peak_src,
                modmul_peak=modmul_peak, cpu_threads=cpu_threads)
     extras = {}
+
+    def block(name, fn, *a, **kw):
+        """One block beside the headline.  A parity failure (SystemExit) always ends the run without a line.  Any other failure
+        of a single-GPU block — out of memory, a full /tmp — is recorded in that block's place and the headline line is still
+        printed; with several ranks a failure must stay fatal (the other ranks would wait in the block's next collective)."""
+        try:
+            extras[name] = fn(*a, **kw)
+        except Exception as e:   # noqa: BLE001 — SystemExit (parity) is not an Exception and passes through
+            if world > 1:
+                raise
+            extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            print("bench.py: block %r failed: %s: %s" % (name, type(e).__name__, e), file=sys.stderr, flush=True)
+
     if not args.no_extras:
         # strong scaling reuses the headline's resident inputs at N = 1
-        extras["strong"] = bench_extras.strong_block(env, headline=(bases, d_scal, n, value, ms_per_step, result))
+        block("strong", bench_extras.strong_block, env, headline=(bases, d_scal, n, value, ms_per_step, result))
         if world == 1:
-            extras["e2e_cold"] = bench_extras.cold_block(env, d_bases, host_np, n, result)
+            block("e2e_cold", bench_extras.cold_block, env, d_bases, host_np, n, result)
     bases.free()
     del d_bases, d_scal, host_scal, host_np
     torch.cuda.empty_cache()
     if not args.no_extras:
         if world == 1:
-            extras["ntt"] = bench_extras.ntt_block(env)
-            extras["sweep"] = bench_extras.sweep_block(env)
-            extras["mulvar"] = bench_extras.mulvar_block(env)
-            extras["params"] = bench_extras.params_block(env)
-        extras["batch"] = bench_extras.batch_block(env)
+            block("ntt", bench_extras.ntt_block, env)
+            block("sweep", bench_extras.sweep_block, env)
+            block("mulvar", bench_extras.mulvar_block, env)
+            block("params", bench_extras.params_block, env)
+        block("batch", bench_extras.batch_block, env)
     if not args.no_prove:
-        extras["prove"] = bench_extras.prove_block(env)
+        block("prove", bench_extras.prove_block, env)
     if line is not None:
         line.update(extras)
     if rank == 0:
