@@ -157,7 +157,11 @@ static int msm_host_split(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, c
     const size_t first_len = std::min(n, (n * (size_t)first_pct / 100 + 1023) & ~(size_t)1023);
     const size_t piece_len = pieces > 1 ? (n - first_len + pieces - 2) / (pieces - 1) : 0;
     std::vector<uint8_t> partials((size_t)pieces * 64, 0);
-    cudaEvent_t copied[2] = {nullptr, nullptr};
+    struct Events {   // released on every exit path
+        cudaEvent_t e[2] = {nullptr, nullptr};
+        ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+        cudaEvent_t& operator[](int i) { return e[i]; }
+    } copied;
     for (int l = 0; l < 2; l++) H2A_CUDA(ctx, cudaEventCreateWithFlags(&copied[l], cudaEventDisableTiming));
     H2A_CUDA(ctx, cudaEventRecord(copied[1], ctx->stream));   // the second lane starts after work already queued here
     H2A_CUDA(ctx, cudaStreamWaitEvent(alt->stream, copied[1], 0));
@@ -191,7 +195,6 @@ static int msm_host_split(h2a_ctx* ctx, const h2a_bases* bases, size_t offset, c
             int r2 = h2a_msm_finish(lanes[l], partials.data() + 64 * pending_piece[l]);
             if (rc == H2A_OK) rc = r2;
         }
-        cudaEventDestroy(copied[l]);
     }
     ctx->profiling = prof;
     ctx->launches += alt->launches;

@@ -211,7 +211,10 @@ int h2a_comm_broadcast_dev(h2a_ctx* ctx, void* d_buf, size_t bytes, int root) {
 int h2a_msm_g1_sharded(h2a_ctx* ctx, const h2a_bases* local_bases, size_t offset, const void* d_local_scalars, size_t n_local,
                        uint8_t out_affine[64]) {
     H2A_DEVICE(ctx);
-    if (!ctx || !local_bases || !out_affine) return H2A_ERR_INVALID;
+    if (!ctx || !local_bases || !out_affine || (!d_local_scalars && n_local)) return H2A_ERR_INVALID;
+    if (offset > local_bases->n || n_local > local_bases->n - offset)
+        H2A_FAIL(ctx, H2A_ERR_INVALID, "msm_g1_sharded: offset %zu + n %zu exceeds %zu local bases", offset, n_local, local_bases->n);
+    if (ctx->comm_world > 64) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm_g1_sharded: more than 64 ranks");
     uint8_t mine[64];
     H2A_TRY(h2a_msm_run(ctx, local_bases, offset, (const uint8_t*)d_local_scalars, n_local, mine));
     if (ctx->comm_world == 1) {
@@ -219,7 +222,6 @@ int h2a_msm_g1_sharded(h2a_ctx* ctx, const h2a_bases* local_bases, size_t offset
         return H2A_OK;
     }
     uint8_t all[64 * 64];
-    if (ctx->comm_world > 64) H2A_FAIL(ctx, H2A_ERR_INVALID, "msm_g1_sharded: more than 64 ranks");
     H2A_TRY(h2a_comm_allgather(ctx, mine, all, 64));
     return h2a_g1_sum(all, (size_t)ctx->comm_world, out_affine);
 }

@@ -333,14 +333,16 @@ int h2a_dev_free(h2a_ctx* ctx, void* dev) {
 }
 int h2a_copy_h2d(h2a_ctx* ctx, void* dev, const void* host, size_t bytes) {
     H2A_DEVICE(ctx);
-    if (!ctx) return H2A_ERR_INVALID;
+    if (!ctx || ((!dev || !host) && bytes)) return H2A_ERR_INVALID;
+    if (!bytes) return H2A_OK;
     H2A_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2A_OK;
 }
 int h2a_copy_d2h(h2a_ctx* ctx, void* host, const void* dev, size_t bytes) {
     H2A_DEVICE(ctx);
-    if (!ctx) return H2A_ERR_INVALID;
+    if (!ctx || ((!dev || !host) && bytes)) return H2A_ERR_INVALID;
+    if (!bytes) return H2A_OK;
     H2A_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     H2A_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return H2A_OK;

@@ -932,6 +932,7 @@ static int set_keys_impl(h2a_ctx* ctx, h2a_circuit* c, const h2a_bases* g, const
     if (!ctx || !c || !g || !g_lagrange || !vk_hash || !coset_shift) return H2A_ERR_INVALID;
     const Shape& s = c->shape;
     const uint32_t n = s.n, m = 1u << s.ext_k;
+    if ((s.n_fixed && !fixed_values) || (!s.perm.empty() && !sigmas)) H2A_FAIL(ctx, H2A_ERR_INVALID, "set_keys: fixed / permutation columns missing");
     if (g->n < n || g_lagrange->n < n) H2A_FAIL(ctx, H2A_ERR_INVALID, "set_keys: params hold fewer than %u bases", n);
     if (s.n_advice > MAX_COLS || s.n_fixed > MAX_COLS || s.n_instance > MAX_COLS || s.aq.size() > MAX_Q || s.fq.size() > MAX_Q ||
         s.iq.size() > MAX_Q || s.lookups.size() > MAX_LK || s.perm.size() > MAX_PERM || s.n_chunks > MAX_CHUNKS || s.chunk_len > 8)
