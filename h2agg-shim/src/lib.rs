@@ -83,6 +83,15 @@ pub fn comm_unique_ids() -> Result<[u8; 256]> {
     Ok(ids)
 }
 
+/// The transcript scalar of a verifying key (src/verifier.rs:341-358) from `format!("{:?}", vk.pinned())`: the `vk_hash`
+/// argument of [`Circuit::set_keys`] / [`Circuit::set_vk`].  Host only.
+pub fn vk_hash(pinned_debug: &str) -> [u8; 32] {
+    let mut out = [0u8; 32];
+    let rc = unsafe { sys::h2a_vk_hash(pinned_debug.as_ptr(), pinned_debug.len(), out.as_mut_ptr()) };
+    assert_eq!(rc, sys::H2A_OK);
+    out
+}
+
 fn bytes_of<T>(s: &[T], elem: usize) -> *const u8 {
     assert_eq!(size_of::<T>(), elem, "element is not {} bytes", elem);
     s.as_ptr() as *const u8

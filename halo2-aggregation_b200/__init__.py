@@ -25,5 +25,6 @@ from .api import (  # noqa: F401
     g1_sum,
     fr_root_of_unity,
     xorshift_scalar,
+    vk_hash,
 )
 from .dist import allgather_points, allgather_sum, make_commitment_exchange, shard_range  # noqa: F401

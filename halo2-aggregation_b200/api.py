@@ -92,6 +92,16 @@ def fr_root_of_unity(k):
     return out
 
 
+def vk_hash(pinned_debug):
+    """h2a_vk_hash: the transcript scalar of a verifying key from `format!("{:?}", vk.pinned())` (src/verifier.rs:341-358)."""
+    data = np.frombuffer(pinned_debug.encode() if isinstance(pinned_debug, str) else bytes(pinned_debug), dtype=np.uint8)
+    out = np.zeros(32, np.uint8)
+    rc = load_library().h2a_vk_hash(_ptr(data) if data.size else None, c_sz(data.size), _ptr(out))
+    if rc != 0:
+        raise H2AError(rc, "vk_hash")
+    return out
+
+
 def xorshift_scalar(seed16):
     """The KZG secret the reference's seeded XorShiftRng yields (examples/simple-example.rs:584-589)."""
     seed = np.frombuffer(bytes(seed16), dtype=np.uint8)

@@ -206,6 +206,22 @@ int h2a_xorshift_scalar(const uint8_t seed[16], uint8_t out_scalar[32]) {
     return H2A_OK;
 }
 
+// `vk.pinned()` hashed into the transcript (src/verifier.rs:341-358): Blake2b-512, personal "Halo2-Verify-Key", over
+// len_le64 || bytes of the Debug string, then Fr::from_bytes_wide.
+int h2a_vk_hash(const uint8_t* pinned_debug, size_t len, uint8_t out_scalar[32]) {
+    if (!out_scalar || (!pinned_debug && len)) return H2A_ERR_INVALID;
+    h2a_glue::Blake2bState st(64, "Halo2-Verify-Key");
+    uint8_t le[8];
+    const uint64_t l64 = (uint64_t)len;
+    memcpy(le, &l64, 8);
+    st.absorb(le, 8);
+    if (len) st.absorb(pinned_debug, len);
+    uint8_t wide[64];
+    st.digest(wide);
+    h2a_host::fr_store(out_scalar, h2a_glue::fr_from_wide(wide));
+    return H2A_OK;
+}
+
 h2a_transcript* h2a_transcript_new(void) { return new h2a_transcript(); }
 void h2a_transcript_free(h2a_transcript* t) { delete t; }
 int h2a_transcript_common_point(h2a_transcript* t, const uint8_t point_affine[64]) {

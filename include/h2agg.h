@@ -268,6 +268,11 @@ int h2a_kzg_setup(h2a_ctx* ctx, uint32_t k, const uint8_t s[32], h2a_bases** out
 /* The scalar that `XorShiftRng::from_seed(seed)` yields for the KZG secret (examples/simple-example.rs:584-589):
  * rand_xorshift 0.3 stream, 64 bytes, Fr::from_bytes_wide (the last step is upstream-inferred). Host only. */
 int h2a_xorshift_scalar(const uint8_t seed[16], uint8_t out_scalar[32]);
+/* The transcript scalar of the verifying key (src/verifier.rs:341-358): Blake2b-512 with personal "Halo2-Verify-Key" over the length
+ * of `pinned_debug` as a little-endian u64 followed by its bytes, reduced with Fr::from_bytes_wide.  `pinned_debug` is the string the
+ * Rust side formats with `format!("{:?}", vk.pinned())`: the dependency's Debug output cannot be produced outside it, the hashing can.
+ * The result is the `vk_hash` argument of h2a_circuit_set_vk / h2a_circuit_set_keys.  Host only; len = 0 hashes the empty string. */
+int h2a_vk_hash(const uint8_t* pinned_debug, size_t len, uint8_t out_scalar[32]);
 /* Copy resident bases back to the host (n * 64 bytes), e.g. to write a params file. */
 int h2a_bases_download(h2a_ctx* ctx, const h2a_bases* bases, uint8_t* out_affine_xy);
 /* Parameter files — `Params::write(&mut file)` / `Params::read(file)` as used at examples/simple-example.rs:679-691 to cache

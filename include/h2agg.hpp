@@ -181,6 +181,14 @@ inline Fr xorshift_scalar(const std::array<uint8_t, 16>& seed) {
     if (rc != H2A_OK) throw Error(rc, "h2a_xorshift_scalar");
     return out;
 }
+// The transcript scalar of a verifying key (src/verifier.rs:341-358) from `format!("{:?}", vk.pinned())`: the vk_hash argument of
+// Circuit::set_keys / Circuit::set_vk.  Host only.
+inline Fr vk_hash(const std::string& pinned_debug) {
+    Fr out;
+    const int rc = h2a_vk_hash(reinterpret_cast<const uint8_t*>(pinned_debug.data()), pinned_debug.size(), out.data());
+    if (rc != H2A_OK) throw Error(rc, "h2a_vk_hash");
+    return out;
+}
 // `EvaluationDomain::get_omega` for 2^k rows.  Host only.
 inline Fr root_of_unity(uint32_t k) {
     Fr out;

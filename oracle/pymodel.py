@@ -263,3 +263,12 @@ REFERENCE_SETUP_SEED = bytes([0x59, 0x62, 0xbe, 0x5d, 0x76, 0x3d, 0x31, 0x8d, 0x
 def setup_secret_from_seed(seed16=REFERENCE_SETUP_SEED):
     """[UPSTREAM-INFERRED] `Fr::random(rng)` of the dependency = from_bytes_wide over 64 bytes of the stream."""
     return int.from_bytes(XorShiftRng(seed16).fill_bytes(64), "little") % R
+
+
+def vk_hash_from_pinned(pinned_debug):
+    """The scalar `VerifierChip` absorbs for the verifying key (src/verifier.rs:341-358): Blake2b-512, personal
+    "Halo2-Verify-Key", over len_le64 || bytes of `format!("{:?}", vk.pinned())`, then Fr::from_bytes_wide."""
+    import hashlib
+    data = pinned_debug.encode() if isinstance(pinned_debug, str) else bytes(pinned_debug)
+    h = hashlib.blake2b(len(data).to_bytes(8, "little") + data, digest_size=64, person=b"Halo2-Verify-Key").digest()
+    return int.from_bytes(h, "little") % R

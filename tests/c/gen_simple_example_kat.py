@@ -127,6 +127,11 @@ def build():
     out.append(carr("KAT_FR_DELTA", frs([pk.DELTA])))
     out.append(carr("KAT_FR_C", frs([c["public_inputs"][0]])))
     out.append(carr("KAT_CHALLENGE", frs([challenge])))
+    # a string of the shape `format!("{:?}", vk.pinned())` takes (longer than one 128-byte Blake2b block; no quotes to escape in C)
+    sample = "PinnedVerificationKey { base_modulus: 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47, domain: PinnedEvaluationDomain { k: 9, extended_k: 11 } } " * 3
+    out.append('static const char KAT_PINNED_SAMPLE[] = "%s";\n' % sample)
+    out.append(carr("KAT_VK_HASH_SAMPLE", frs([pm.vk_hash_from_pinned(sample)])))
+    out.append(carr("KAT_VK_HASH_EMPTY", frs([pm.vk_hash_from_pinned("")])))
     out.append("static const unsigned KAT_MAPPING_MOVED[%d][2] = {%s};\n" % (len(moved), ", ".join("{%d, %d}" % m for m in moved)))
     out.append(carr("KAT_G1", pts([pm.G1])))
     out.append(carr("KAT_TWO_G", pts([pm.g1_mul(pm.G1, 2)])))

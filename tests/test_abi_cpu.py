@@ -181,6 +181,22 @@ def test_tree_halves_never_share_a_region():
 
 
 # ---- the boundary as other languages see it: the Rust crates and a plain C program
+def test_vk_hash_matches_hashlib_and_model():
+    """Row a9: the scalar the verifier absorbs for the verifying key (src/verifier.rs:341-358) — Blake2b-512 with personal
+    "Halo2-Verify-Key" over len_le64 || Debug string, then Fr::from_bytes_wide — from the library, the oracle's model and hashlib
+    directly, at lengths on both sides of the 128-byte block boundaries (the length prefix shifts them by 8)."""
+    import hashlib
+    rng = random.Random(9)
+    for ln in (0, 1, 7, 119, 120, 121, 127, 128, 129, 247, 248, 249, 1000, 5000):
+        data = bytes(rng.randrange(32, 127) for _ in range(ln))
+        h = hashlib.blake2b(ln.to_bytes(8, "little") + data, digest_size=64, person=b"Halo2-Verify-Key").digest()
+        want = int.from_bytes(h, "little") % pm.R
+        assert pm.vk_hash_from_pinned(data) == want
+        assert pm.fr_from_mont_bytes(h2a.vk_hash(data)) == want, ln
+    assert pm.fr_from_mont_bytes(h2a.vk_hash("PinnedVerificationKey { k: 9 }")) == pm.vk_hash_from_pinned("PinnedVerificationKey { k: 9 }")
+    assert h2a.load_library().h2a_vk_hash(None, 5, None) == -1
+
+
 def _run_tool(*args):
     import subprocess
     import sys
