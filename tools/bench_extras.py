@@ -314,6 +314,28 @@ def params_block(env):
     return out
 
 
+def prove_roofline(op_counts, k, ext_k, table_bits, seconds, modmul_peak, hbm_peak, peak_src):
+    """SURVEY §8d for the prove metric: the algorithmic bytes and Montgomery products of the MSMs and transforms of one proof
+    (MSM: 96 B and ceil(254 / c) batched-affine additions of 6 products per point; NTT: 64 B per element and (m / 2) log2 m
+    butterfly products), summed over op_counts, over the wall time of the proof.  Pure arithmetic (tests/test_bench_helpers.py)."""
+    n, m = 1 << k, 1 << ext_k
+    windows = (254 + table_bits - 1) // table_bits
+    msm_products = op_counts["msm_n"] * n * windows * MODMUL_PER_ADD
+    ntt_products = op_counts["ifft_n"] * (n // 2) * k + (op_counts["coset_fft_4n"] + op_counts["ifft_4n"]) * (m // 2) * ext_k
+    nbytes = op_counts["msm_n"] * n * 96 + op_counts["ifft_n"] * n * 64 + (op_counts["coset_fft_4n"] + op_counts["ifft_4n"]) * m * 64
+    gbs = nbytes / seconds / 1e9
+    gmul = (msm_products + ntt_products) / seconds / 1e9
+    return ({"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if hbm_peak else None, "traffic": None,
+             "peak_source": peak_src, "algorithmic_bytes": nbytes,
+             "note": "96 B per MSM point + 64 B per transformed element, each once, over the wall time of one proof; the pipeline is bound by the "
+                     "integer pipe, see int_pipe"},
+            {"achieved": gmul, "peak": modmul_peak, "unit": "1e9 Montgomery products/s", "frac": gmul / modmul_peak if modmul_peak else None,
+             "algorithmic": "%d MSM products (%d windows of %d bits) + %d butterfly products" % (msm_products, windows, table_bits, ntt_products),
+             "note": "an UPPER estimate of the pipe's use: advice columns of the aggregation profile hold range-checked small values whose "
+                     "upper window digits are zero and are skipped, and quotient / grand-product / evaluation products are not counted; the "
+                     "figure for full-width scalars is the headline's int_pipe"})
+
+
 def prove_block(env):
     """`agg-circuit prove s at k=20`: the prover pipeline at every N, the proof checked by the oracle's verifier."""
     import prove_bench
@@ -348,6 +370,12 @@ def prove_block(env):
                            "(coefficient forms broadcast, extended forms sent as row windows), quotient row-parallel; permutation grand products, "
                            "evaluations and openings replicated" % world,
            "nvlink_traffic_this_rank": pr.get("nvlink_traffic_this_rank")}
+    try:   # roofline fractions of the whole proof (algorithmic figures of SURVEY §8d); never worth losing the block for
+        ext_k = args.prove_k + 2    # degree 5: the quotient lives on 4n points
+        out["roofline"], out["int_pipe"] = prove_roofline(pr["op_counts"], args.prove_k, ext_k, int(pr["config"]["msm_tables"]), value,
+                                                           env["modmul_peak"] * world, env["hbm_peak"] * world, env["peak_src"] + (" x %d GPUs" % world if world > 1 else ""))
+    except Exception as e:   # noqa: BLE001
+        out["roofline"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # CPU figure: the MSM / FFT sequence of create_proof replayed with the oracle's best_multiexp / best_fft
         k = args.prove_k
