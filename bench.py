@@ -89,6 +89,34 @@ def clocks_monitor_stop(proc, t_begin, t_end):
             "window": window, "reasons": reasons}
 
 
+def bind_to_gpu_numa(torch, local_rank):
+    """Several ranks on one host: run this rank — and so first-touch the pinned staging buffers it allocates — on the cores NVML
+    reports as local to its GPU, so that eight ranks' host<->device copies do not all cross the socket interconnect from one
+    memory node (SCALE_r01: e2e efficiency 0.82 at 8 GPUs with device-resident efficiency 0.97).  Returns the CPU list, or None
+    when nothing was changed (no NVML, one node, a cpuset that does not meet the GPU's cores, H2A_BENCH_NUMA=0)."""
+    if os.environ.get("H2A_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local_rank)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByPciBusId("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:   # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if len(cpus) < 2 or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:   # noqa: BLE001 — placement is an optimisation, never a reason to fail
+        return None
+
+
 def oracle_sum(orc, points64):
     """Sum of 64-byte affine points with the oracle's own group law (rank-ordered, like the library's combine)."""
     acc = np.zeros(64, np.uint8)
@@ -156,6 +184,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
     dist = None
+    numa_cpus = bind_to_gpu_numa(torch, local_rank) if world > 1 else None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -309,7 +338,9 @@ def main():
                        "curve": "BN254 G1", "window_bits": c, "windows": windows,
                        "bases": "resident in HBM" + ("" if args.no_precompute else " with per-Params window tables 2^(c*w)*P_i (%.1f GB, built once by h2a_bases_precompute, outside the timed region; see e2e_cold)" % (windows * n * 64 / 1e9)),
                        "l2": "inputs %.0f MB per step exceed the 126 MB L2" % (ALGO_BYTES_PER_POINT * n / 1e6),
-                       "e2e_bases": "resident in HBM (uploaded once, like Params); scalars come from pinned host memory every step"},
+                       "e2e_bases": "resident in HBM (uploaded once, like Params); scalars come from pinned host memory every step",
+                       "host_placement": ("rank 0 runs on the %d cores NVML reports as local to its GPU (pinned buffers first-touched there); "
+                                          "every rank does the same" % len(numa_cpus)) if numa_cpus else "default"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128 * 64,
                     "ms_per_step": e2e_ms / args.steps},

@@ -24,3 +24,45 @@ def test_prove_roofline_on_the_recorded_line():
     ntt = cnt["ifft_n"] * (n // 2) * 20 + (cnt["coset_fft_4n"] + cnt["ifft_4n"]) * (m // 2) * 22
     assert abs(pipe["achieved"] - (msm + ntt) / pr["value"] / 1e9) < 1e-6
     assert 0 < pipe["frac"] < 1.0 and "UPPER" in pipe["note"]
+
+
+def test_numa_placement_picks_the_gpu_local_cores(monkeypatch):
+    """bench.py at N > 1 runs each rank on the cores NVML reports as local to its GPU: the mask-to-CPU-set logic with a fake NVML
+    (half of the allowed cores), the refusals (no NVML, a mask equal to what is already allowed, the switch), affinity restored."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    allowed = sorted(os.sched_getaffinity(0))
+    if len(allowed) < 4:
+        import pytest
+        pytest.skip("needs four cores to split")
+    half = allowed[:len(allowed) // 2]
+    words = (max(os.cpu_count() or 1, 1) + 63) // 64
+
+    def mask_of(cpus):
+        out = [0] * words
+        for c in cpus:
+            out[c // 64] |= 1 << (c % 64)
+        return out
+
+    state = {"mask": mask_of(half)}
+    fake = types.SimpleNamespace(nvmlInit=lambda: None, nvmlDeviceGetHandleByPciBusId=lambda s: ("h", s), nvmlDeviceGetHandleByIndex=lambda i: ("h", i),
+                                 nvmlDeviceGetCpuAffinity=lambda h, n: state["mask"][:n])
+    props = types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0)
+    torch = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: props))
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    try:
+        assert bench.bind_to_gpu_numa(torch, 0) == half and sorted(os.sched_getaffinity(0)) == half
+        os.sched_setaffinity(0, allowed)
+        state["mask"] = mask_of(allowed)                      # one memory node: nothing to do
+        assert bench.bind_to_gpu_numa(torch, 0) is None and sorted(os.sched_getaffinity(0)) == allowed
+        state["mask"] = mask_of(half)
+        monkeypatch.setenv("H2A_BENCH_NUMA", "0")
+        assert bench.bind_to_gpu_numa(torch, 0) is None
+        monkeypatch.delenv("H2A_BENCH_NUMA")
+        fake.nvmlInit = lambda: (_ for _ in ()).throw(RuntimeError("no NVML"))
+        assert bench.bind_to_gpu_numa(torch, 0) is None and sorted(os.sched_getaffinity(0)) == allowed
+    finally:
+        os.sched_setaffinity(0, allowed)
